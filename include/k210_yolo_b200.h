@@ -1,0 +1,148 @@
+/* k210_yolo_b200 — C-ABI of the B200-native YOLOv3 inference hot path.
+ *
+ * Drop-in boundary for the path  keras_inference.py:main -> network(...) -> predict ->
+ * decode -> per-class NMS  of zhen8838/K210_Yolo_framework.  Every entry point names the
+ * reference interface it replaces (paths under /root/reference).  Plain pointers and sizes
+ * only; device pointers come from the caller (e.g. torch.Tensor.data_ptr()), streams are
+ * cudaStream_t passed as void*.  All functions return K2Y_OK (0) or a negative error code;
+ * k2y_last_error() gives the message.  There is NO CPU fallback: calls that need a GPU fail
+ * with K2Y_ERR_CUDA when none is present.
+ */
+#ifndef K210_YOLO_B200_H
+#define K210_YOLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define K2Y_OK 0
+#define K2Y_ERR_INVALID (-1)   /* bad argument / unknown name / shape mismatch */
+#define K2Y_ERR_CUDA (-2)      /* CUDA runtime or driver error (incl. no device) */
+#define K2Y_ERR_STATE (-3)     /* call order violated (e.g. run before finalize/bind) */
+#define K2Y_ERR_NOMEM (-4)
+
+/* Arithmetic of the dense (1x1 / 3x3) convolutions. */
+#define K2Y_MATH_FP32_SIMT 0   /* fp32 FFMA on CUDA cores (exact-order reference path on the GPU) */
+#define K2Y_MATH_TC_3XTF32 1   /* tcgen05 kind::tf32, hi/lo split x3 (fp32-class accuracy) */
+#define K2Y_MATH_TC_TF32 2     /* tcgen05 kind::tf32, single pass */
+
+const char *k2y_last_error(void);
+int k2y_version(void);
+/* 1 if a CUDA device is usable, 0 otherwise (never fails). */
+int k2y_cuda_available(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Network = the reference's model-builder "plugin" API
+ *   network(input_shape=[H,W,3], anchor_num, class_num, alpha=) -> (yolo_model, yolo_model_warpper)
+ *   models/yolonet.py:12 (yolo_mobilev1), :49 (yolo_mobilev2), :107 (tiny_yolo), :161 (yolo)
+ * and the two methods keras_inference.py uses on it: load_weights (:80) and predict (:88).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct k2y_net k2y_net;
+
+/* Builds the layer graph (native graph builder).  model_def is one of the four reference
+ * builder names.  Output grids are derived from the input size (H/32, H/16[, H/8]) rather than
+ * the reference's hard-coded Reshape targets (yolonet.py:40-41,98-99,140-141,175-177). */
+int k2y_net_create(const char *model_def, int in_h, int in_w, float alpha, int anchor_num, int class_num,
+                   int max_batch, int device, k2y_net **out);
+int k2y_net_destroy(k2y_net *net);
+
+/* Weighted layers, in creation order (== Keras auto-naming order). */
+typedef struct {
+    char name[64];     /* Keras layer name of the conv ("conv_pw_3", "conv2d_1", ...) */
+    char bn_name[64];  /* Keras name of the BatchNormalization folded behind it, "" if none */
+    int32_t kind;      /* 0 dense conv, 1 depthwise conv */
+    int32_t kh, kw, cin, cout, stride;
+    int32_t has_bias;
+} k2y_layer_info;
+int k2y_net_num_layers(const k2y_net *net, int *n);
+int k2y_net_layer_info(const k2y_net *net, int i, k2y_layer_info *info);
+
+/* load_weights (keras_inference.py:80): one call per Keras variable.  layer is the Keras layer
+ * name as stored in the HDF5 file, var one of kernel | depthwise_kernel | bias | gamma | beta |
+ * moving_mean | moving_variance; data is host float32 in the Keras layout (HWIO kernels,
+ * depthwise (3,3,C,1)); dims/ndim are checked against the graph.  Unknown layer -> K2Y_ERR_INVALID. */
+int k2y_net_set_weight(k2y_net *net, const char *layer, const char *var, const float *data,
+                       const int64_t *dims, int ndim);
+/* Folds BatchNormalization (eps 1e-3) into per-channel scale/shift, packs and uploads.  Fails with
+ * K2Y_ERR_STATE naming the first variable that was never set. */
+int k2y_net_finalize(k2y_net *net);
+
+int k2y_net_set_math(k2y_net *net, int math_mode);
+int k2y_net_get_math(const k2y_net *net, int *math_mode);
+/* 1 (default) = replay the layer schedule as one CUDA graph per batch size; 0 = plain launches. */
+int k2y_net_set_use_graph(k2y_net *net, int use_graph);
+
+int k2y_net_num_outputs(const k2y_net *net, int *n);
+/* Per-image shape of head l of the plain yolo_model: [h, w, anchor_num*(5+class_num)]. */
+int k2y_net_output_shape(const k2y_net *net, int l, int *h, int *w, int *c);
+/* Bytes of activation arena needed for max_batch images. */
+int k2y_net_workspace_bytes(const k2y_net *net, size_t *bytes);
+/* Binds caller-owned device storage: workspace (>= workspace_bytes, 256-B aligned), the input
+ * x [max_batch,H,W,3] f32 NHWC and one buffer per head [max_batch,h,w,c] f32 NHWC. */
+int k2y_net_bind(k2y_net *net, void *workspace, size_t workspace_bytes, const float *x_dev,
+                 float *const *heads_dev, int n_heads);
+/* predict on bound device buffers (keras_inference.py:88), asynchronous on `stream`. */
+int k2y_net_run(k2y_net *net, int batch, void *stream);
+/* predict with HOST buffers: H2D of x, run, D2H of every head, stream-synchronised on return.
+ * x_host [batch,H,W,3] f32; heads_host[l] [batch,h_l,w_l,c] f32. */
+int k2y_net_predict_host(k2y_net *net, const float *x_host, int batch, float *const *heads_host, void *stream);
+/* Kernel launches (graph nodes) one k2y_net_run(batch) issues. */
+int k2y_net_launches_per_run(const k2y_net *net, int *n);
+/* Debug/parity hook: copies the (post-activation) output of the conv layer `name` for the last run
+ * into host memory as [batch,h,w,c] f32.  Only valid with use_graph == 0 and keep_all (below). */
+int k2y_net_set_keep_all(k2y_net *net, int keep_all);
+int k2y_net_read_layer(k2y_net *net, const char *name, int batch, float *host, size_t host_floats, int *h,
+                       int *w, int *c);
+
+/* ------------------------------------------------------------------------------------------
+ * KERAS-dialect decode + per-class NMS  (keras_inference.py:94-135; tools/utils.py:524-547
+ * tf_xywh_to_all; keras_inference.py:32-72 correct_box; tf.image.non_max_suppression).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    float ymin, xmin, ymax, xmax; /* pixels of the ORIGINAL image, as correct_box returns */
+    float score;                  /* sigmoid(cls) * sigmoid(conf) */
+    int32_t index;                /* flat box index: off_l + (row*W_l + col)*A + a, layer 0 first */
+} k2y_det;
+
+typedef struct {
+    int32_t n_layers;          /* <= 3 */
+    int32_t layer_h[3], layer_w[3];
+    int32_t anchor_num, class_num;
+    float anchors[3 * 8 * 2];  /* [layer][anchor][(w,h)] fraction of the net input (Helper.anchors) */
+    int32_t in_h, in_w;        /* network input size (image_size) */
+    float obj_thresh;          /* candidate iff score >= obj_thresh */
+    float iou_thresh;          /* suppressed iff IoU > iou_thresh */
+    int32_t max_per_class;     /* tf.image.non_max_suppression max_output_size (30) */
+} k2y_detect_cfg;
+
+/* Scratch bytes k2y_detect_keras needs for `batch` images. */
+int k2y_detect_workspace_bytes(const k2y_detect_cfg *cfg, int batch, size_t *bytes);
+/* heads_dev[l]: [batch,h_l,w_l,A*(5+C)] f32 NHWC device tensors.  image_hw_dev: [batch,2] f32
+ * (orig_h, orig_w) on device.  Outputs (device): dets [batch][C][max_per_class], counts [batch][C].
+ * Records of one class are in descending score (ties: ascending index). */
+int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *heads_dev, int batch,
+                     const float *image_hw_dev, k2y_det *dets_dev, int32_t *counts_dev, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * REGION_C-dialect decode + NMS, batched on device  (region_layer.c:121-283 per layer).
+ * in_dev: [batch][A][5+C][H][W] f32 planar.  Outputs (device): probs [batch][N][C+1] after NMS,
+ * boxes [batch][N][4] (x,y,w,h centre form, letterbox-corrected), N = A*H*W, index = a*H*W+row*W+col.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t layer_w, layer_h, anchor_num, classes;
+    int32_t net_w, net_h, image_w, image_h;
+    float anchors[8 * 2];
+    float threshold, nms_value;
+} k2y_region_cfg;
+int k2y_region_workspace_bytes(const k2y_region_cfg *cfg, int batch, size_t *bytes);
+int k2y_region_run(const k2y_region_cfg *cfg, const float *in_dev, int batch, float *out_dev /* activations, may be NULL */,
+                   float *probs_dev, float *boxes_dev, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* K210_YOLO_B200_H */

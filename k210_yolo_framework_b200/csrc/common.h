@@ -1,0 +1,74 @@
+// Shared declarations for libk210yolo_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/k210_yolo_b200.h"
+
+namespace k2y {
+
+void set_error(const char *fmt, ...);
+
+#define K2Y_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            k2y::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return K2Y_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_RELU6 = 3 };
+
+// One dense convolution (1x1 or 3x3) as an implicit GEMM over NHWC fp32 activations:
+//   dst[b,oy,ox,n] = act( scale[n] * sum_{ky,kx,ci} in[b, oy*s-pad_t+ky, ox*s-pad_l+kx, ci] * w[(ky,kx,ci), n] + shift[n] ) (+ residual)
+// where `in` is the channel-concatenation of src0 (optionally nearest-upsampled x2) and src1.
+struct ConvArgs {
+    const float *src0;
+    const float *src1;      // nullptr when there is no concat
+    const float *residual;  // nullptr when there is no Add
+    float *dst;
+    const float *w;         // [K][N] row-major, K = kh*kw*(C0+C1) ordered (ky,kx,ci)  (== Keras HWIO flattened)
+    const float *scale;     // [N]
+    const float *shift;     // [N]
+    int B, H, W;            // logical input extent (after upsampling src0)
+    int C0, C1;
+    int up0;                // src0 stored at (H/2, W/2)
+    int OH, OW, N;
+    int kh, kw, stride, pad_t, pad_l;
+    int act;
+    float alpha;
+};
+
+struct DwArgs {
+    const float *src;
+    float *dst;
+    const float *w;      // [9][C]
+    const float *scale;  // [C]
+    const float *shift;  // [C]
+    int B, H, W, C, OH, OW, stride, pad_t, pad_l;
+    int act;
+    float alpha;
+};
+
+struct PoolArgs {
+    const float *src;
+    float *dst;
+    int B, H, W, C, OH, OW, stride;  // 2x2 window, SAME (pads bottom/right with -inf)
+};
+
+// fp32 CUDA-core kernels (conv_simt.cu)
+cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st);
+cudaError_t launch_dwconv(const DwArgs &a, cudaStream_t st);
+cudaError_t launch_maxpool(const PoolArgs &a, cudaStream_t st);
+
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+    if (act == ACT_LEAKY) return v >= 0.f ? v : v * alpha;
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+    return v;
+}
+
+}  // namespace k2y

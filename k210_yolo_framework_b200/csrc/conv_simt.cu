@@ -1,0 +1,310 @@
+// fp32 CUDA-core convolution kernels (K2Y_MATH_FP32_SIMT): implicit-GEMM dense conv with
+// fused concat / nearest-upsample loader and BN+activation(+residual) epilogue, depthwise 3x3,
+// 2x2 max-pool.  These are the exact-fp32 GPU path every tensor-core kernel is validated
+// against, and the path for shapes the tcgen05 kernels do not cover (Cin = 3 first conv).
+//
+// Replaces the TF ops the reference reaches through keras predict (keras_inference.py:88):
+// Conv2D / DepthwiseConv2dNative / FusedBatchNorm / LeakyRelu / Relu(6) / ResizeNearestNeighbor /
+// ConcatV2 / MaxPool / Add, as composed by models/yolonet.py and models/keras_mobilenet*.py.
+#include "common.h"
+
+namespace k2y {
+
+namespace {
+
+constexpr int BN_T = 64;
+constexpr int BK_T = 16;
+
+__device__ __forceinline__ const float *src_ptr(const ConvArgs &a, int b, int iy, int ix, int ci) {
+    // (iy, ix) are in-bounds logical coordinates; ci indexes the concatenated channel axis.
+    if (ci < a.C0) {
+        if (a.up0) {
+            const int h2 = a.H >> 1, w2 = a.W >> 1;
+            return a.src0 + ((size_t)(b * h2 + (iy >> 1)) * w2 + (ix >> 1)) * a.C0 + ci;
+        }
+        return a.src0 + ((size_t)(b * a.H + iy) * a.W + ix) * a.C0 + ci;
+    }
+    return a.src1 + ((size_t)(b * a.H + iy) * a.W + ix) * a.C1 + (ci - a.C0);
+}
+
+template <int TM, bool VEC>
+__global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const ConvArgs a) {
+    constexpr int BM = 16 * TM;
+    constexpr int A_PER_T = VEC ? (BM / 64) : (BM / 16);  // float4s or scalars of A per thread per k-tile
+    __shared__ __align__(16) float As[BK_T][BM + 4];
+    __shared__ __align__(16) float Bs[BK_T][BN_T];
+
+    const int tid = threadIdx.x;
+    const int M = a.B * a.OH * a.OW;
+    const int Cin = a.C0 + a.C1;
+    const int K = a.kh * a.kw * Cin;
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN_T;
+
+    // Per-thread A-load coordinates (fixed over the K loop).
+    int pb[A_PER_T], py[A_PER_T], px[A_PER_T];
+#pragma unroll
+    for (int i = 0; i < A_PER_T; ++i) {
+        const int m_l = VEC ? ((tid >> 2) + 64 * i) : ((tid >> 4) + 16 * i);
+        const int m = m0 + m_l;
+        if (m < M) {
+            const int ox = m % a.OW;
+            const int t = m / a.OW;
+            const int oy = t % a.OH;
+            pb[i] = t / a.OH;
+            py[i] = oy * a.stride - a.pad_t;
+            px[i] = ox * a.stride - a.pad_l;
+        } else {
+            pb[i] = -1;
+            py[i] = 0;
+            px[i] = 0;
+        }
+    }
+    const int ak = VEC ? ((tid & 3) * 4) : (tid & 15);  // k offset inside the tile
+    const int bk = tid >> 4;                            // B tile: row
+    const int bn = (tid & 15) * 4;                      // B tile: first col
+    const bool n_vec = (a.N & 3) == 0;
+
+    float4 ra[VEC ? A_PER_T : 1];
+    float rs[VEC ? 1 : A_PER_T];
+    float4 rb;
+
+    auto load_tiles = [&](int k0) {
+        // ---- A ----
+        const int k = k0 + ak;
+        int ky = 0, kx = 0, ci = 0;
+        const bool kin = k < K;
+        if (kin) {
+            const int tap = k / Cin;
+            ci = k - tap * Cin;
+            ky = tap / a.kw;
+            kx = tap - ky * a.kw;
+        }
+#pragma unroll
+        for (int i = 0; i < A_PER_T; ++i) {
+            const int iy = py[i] + ky, ix = px[i] + kx;
+            const bool ok = kin && pb[i] >= 0 && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+            if (VEC) {
+                ra[VEC ? i : 0] = ok ? __ldg(reinterpret_cast<const float4 *>(src_ptr(a, pb[i], iy, ix, ci)))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                rs[VEC ? 0 : i] = ok ? __ldg(src_ptr(a, pb[i], iy, ix, ci)) : 0.f;
+            }
+        }
+        // ---- B ----
+        const int kk = k0 + bk;
+        const int n = n0 + bn;
+        if (kk < K && n_vec && n + 3 < a.N) {
+            rb = __ldg(reinterpret_cast<const float4 *>(a.w + (size_t)kk * a.N + n));
+        } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            if (kk < K) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < a.N) t[j] = __ldg(a.w + (size_t)kk * a.N + n + j);
+            }
+            rb = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int i = 0; i < A_PER_T; ++i) {
+            if (VEC) {
+                const int m_l = (tid >> 2) + 64 * i;
+                const float4 v = ra[VEC ? i : 0];
+                As[ak + 0][m_l] = v.x;
+                As[ak + 1][m_l] = v.y;
+                As[ak + 2][m_l] = v.z;
+                As[ak + 3][m_l] = v.w;
+            } else {
+                const int m_l = (tid >> 4) + 16 * i;
+                As[ak][m_l] = rs[VEC ? 0 : i];
+            }
+        }
+        *reinterpret_cast<float4 *>(&Bs[bk][bn]) = rb;
+    };
+
+    float acc[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int ty = tid >> 4, tx = tid & 15;
+    load_tiles(0);
+    store_tiles();
+    __syncthreads();
+    for (int k0 = 0; k0 < K; k0 += BK_T) {
+        const bool more = k0 + BK_T < K;
+        if (more) load_tiles(k0 + BK_T);
+#pragma unroll
+        for (int kk = 0; kk < BK_T; ++kk) {
+            float av[TM];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(&As[kk][ty * TM + i]);
+                av[i] = v.x;
+                av[i + 1] = v.y;
+                av[i + 2] = v.z;
+                av[i + 3] = v.w;
+            }
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                acc[i][0] = fmaf(av[i], bv.x, acc[i][0]);
+                acc[i][1] = fmaf(av[i], bv.y, acc[i][1]);
+                acc[i][2] = fmaf(av[i], bv.z, acc[i][2]);
+                acc[i][3] = fmaf(av[i], bv.w, acc[i][3]);
+            }
+        }
+        __syncthreads();
+        if (more) {
+            store_tiles();
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue: folded BN / bias, activation, residual ----
+    const int n = n0 + tx * 4;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = (n + j < a.N) ? __ldg(a.scale + n + j) : 0.f;
+        sh[j] = (n + j < a.N) ? __ldg(a.shift + n + j) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = apply_act(fmaf(acc[i][j], sc[j], sh[j]), a.act, a.alpha);
+        float *out = a.dst + (size_t)m * a.N + n;
+        if (n_vec && n + 3 < a.N) {
+            if (a.residual) {
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(a.residual + (size_t)m * a.N + n));
+                v[0] += r.x;
+                v[1] += r.y;
+                v[2] += r.z;
+                v[3] += r.w;
+            }
+            *reinterpret_cast<float4 *>(out) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j < a.N) {
+                    float r = a.residual ? __ldg(a.residual + (size_t)m * a.N + n + j) : 0.f;
+                    out[j] = v[j] + r;
+                }
+        }
+    }
+}
+
+// Depthwise 3x3: one thread per (output pixel, 4 channels).
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs a) {
+    const int c4n = a.C >> 2;
+    const size_t total = (size_t)a.B * a.OH * a.OW * c4n;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % c4n) * 4;
+    size_t p = idx / c4n;
+    const int ox = (int)(p % a.OW);
+    p /= a.OW;
+    const int oy = (int)(p % a.OH);
+    const int b = (int)(p / a.OH);
+    const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= a.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ix0 + kx;
+            if (ix < 0 || ix >= a.W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(a.src + ((size_t)(b * a.H + iy) * a.W + ix) * a.C + c));
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(a.w + (ky * 3 + kx) * a.C + c));
+            acc.x = fmaf(v.x, w.x, acc.x);
+            acc.y = fmaf(v.y, w.y, acc.y);
+            acc.z = fmaf(v.z, w.z, acc.z);
+            acc.w = fmaf(v.w, w.w, acc.w);
+        }
+    }
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4 *>(a.shift + c));
+    float4 o;
+    o.x = apply_act(fmaf(acc.x, sc.x, sh.x), a.act, a.alpha);
+    o.y = apply_act(fmaf(acc.y, sc.y, sh.y), a.act, a.alpha);
+    o.z = apply_act(fmaf(acc.z, sc.z, sh.z), a.act, a.alpha);
+    o.w = apply_act(fmaf(acc.w, sc.w, sh.w), a.act, a.alpha);
+    *reinterpret_cast<float4 *>(a.dst + ((size_t)(b * a.OH + oy) * a.OW + ox) * a.C + c) = o;
+}
+
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const PoolArgs a) {
+    const int c4n = a.C >> 2;
+    const size_t total = (size_t)a.B * a.OH * a.OW * c4n;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % c4n) * 4;
+    size_t p = idx / c4n;
+    const int ox = (int)(p % a.OW);
+    p /= a.OW;
+    const int oy = (int)(p % a.OH);
+    const int b = (int)(p / a.OH);
+    const float ninf = -__int_as_float(0x7f800000);
+    float4 m = make_float4(ninf, ninf, ninf, ninf);
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+        const int iy = oy * a.stride + ky;
+        if (iy >= a.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx) {
+            const int ix = ox * a.stride + kx;
+            if (ix >= a.W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(a.src + ((size_t)(b * a.H + iy) * a.W + ix) * a.C + c));
+            m.x = fmaxf(m.x, v.x);
+            m.y = fmaxf(m.y, v.y);
+            m.z = fmaxf(m.z, v.z);
+            m.w = fmaxf(m.w, v.w);
+        }
+    }
+    *reinterpret_cast<float4 *>(a.dst + ((size_t)(b * a.OH + oy) * a.OW + ox) * a.C + c) = m;
+}
+
+}  // namespace
+
+cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
+    const int M = a.B * a.OH * a.OW;
+    const bool vec = (a.C0 % 4 == 0) && (a.C1 % 4 == 0);
+    const int gy = (a.N + BN_T - 1) / BN_T;
+    // Small-M layers (7x10 / 14x20 grids) use 64-row tiles so that the grid still covers 148 SMs.
+    const bool small = ((M + 127) / 128) * gy < 296;
+    if (small) {
+        dim3 grid((M + 63) / 64, gy);
+        if (vec)
+            conv_igemm_simt_kernel<4, true><<<grid, 256, 0, st>>>(a);
+        else
+            conv_igemm_simt_kernel<4, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid((M + 127) / 128, gy);
+        if (vec)
+            conv_igemm_simt_kernel<8, true><<<grid, 256, 0, st>>>(a);
+        else
+            conv_igemm_simt_kernel<8, false><<<grid, 256, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dwconv(const DwArgs &a, cudaStream_t st) {
+    const size_t total = (size_t)a.B * a.OH * a.OW * (a.C / 4);
+    dwconv3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool(const PoolArgs &a, cudaStream_t st) {
+    const size_t total = (size_t)a.B * a.OH * a.OW * (a.C / 4);
+    maxpool2x2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace k2y

@@ -1,0 +1,483 @@
+// Fused decode + per-class greedy NMS, both dialects of the reference:
+//   KERAS    keras_inference.py:94-135 (+ tools/utils.py:524-547, keras_inference.py:32-72)
+//   REGION_C yolo3_frame_test_public/region_layer.c:121-283
+// One CTA per image.  Phase 1 (all threads): sigmoid/exp/anchor-scale decode of every box, scores
+// written class-major so that phase 2 scans them coalesced.  Phase 2 (one warp per class):
+// ballot-compaction of the candidates in index order, warp bitonic sort on (score desc, index asc)
+// keys, then greedy IoU suppression with the selected boxes held one per lane, so that testing a
+// candidate against <= 32 kept boxes is a single ballot.  Final records are written contiguously
+// per (image, class).
+//
+// Arithmetic is float32 in the reference's operation order with explicit round-to-nearest
+// intrinsics where FMA contraction would change a rounding, so survivor sets are bit-identical to
+// the oracle's whenever the transcendental results (expf) agree.
+#include "common.h"
+
+namespace k2y {
+
+namespace {
+
+constexpr int DET_THREADS = 1024;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ unsigned long long pack_key(float score, int idx) {
+    // scores are > 0 here, so the IEEE bit pattern is monotonic; larger key == earlier in the order
+    return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xffffffffu - (unsigned)idx);
+}
+__device__ __forceinline__ int key_index(unsigned long long k) { return (int)(0xffffffffu - (unsigned)(k & 0xffffffffull)); }
+__device__ __forceinline__ float key_score(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
+
+// Sort (descending) n <= 32 keys held one per lane (lanes >= n hold 0).
+__device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(FULL, key, j);
+            const bool up = ((lane & k) == 0);      // this k-block sorts descending
+            const bool lower = ((lane & j) == 0);   // this lane keeps the "first" element
+            const bool take_max = (up == lower);
+            key = take_max ? (key > other ? key : other) : (key < other ? key : other);
+        }
+    }
+    return key;
+}
+
+// Bitonic sort (descending) of P (power of two) keys in memory by one warp.
+__device__ __forceinline__ void warp_sort_desc_mem(unsigned long long *keys, int P, int lane) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P; i += 32) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// tf.image.non_max_suppression IoU on (ymin,xmin,ymax,xmax) boxes.
+__device__ __forceinline__ float iou_yxyx(const float4 a, const float4 b) {
+    const float ymin_a = fminf(a.x, a.z), ymax_a = fmaxf(a.x, a.z);
+    const float xmin_a = fminf(a.y, a.w), xmax_a = fmaxf(a.y, a.w);
+    const float ymin_b = fminf(b.x, b.z), ymax_b = fmaxf(b.x, b.z);
+    const float xmin_b = fminf(b.y, b.w), xmax_b = fmaxf(b.y, b.w);
+    const float area_a = __fmul_rn(__fsub_rn(ymax_a, ymin_a), __fsub_rn(xmax_a, xmin_a));
+    const float area_b = __fmul_rn(__fsub_rn(ymax_b, ymin_b), __fsub_rn(xmax_b, xmin_b));
+    if (area_a <= 0.f || area_b <= 0.f) return 0.f;
+    const float iy = fmaxf(__fsub_rn(fminf(ymax_a, ymax_b), fmaxf(ymin_a, ymin_b)), 0.f);
+    const float ix = fmaxf(__fsub_rn(fminf(xmax_a, xmax_b), fmaxf(xmin_a, xmin_b)), 0.f);
+    const float inter = __fmul_rn(iy, ix);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+
+// region_layer.c box_iou on centre-form (x,y,w,h) boxes (:228-254).
+__device__ __forceinline__ float overlap_c(float x1, float w1, float x2, float w2) {
+    const float l1 = __fsub_rn(x1, __fmul_rn(w1, 0.5f));
+    const float l2 = __fsub_rn(x2, __fmul_rn(w2, 0.5f));
+    const float left = l1 > l2 ? l1 : l2;
+    const float r1 = __fadd_rn(x1, __fmul_rn(w1, 0.5f));
+    const float r2 = __fadd_rn(x2, __fmul_rn(w2, 0.5f));
+    const float right = r1 < r2 ? r1 : r2;
+    return __fsub_rn(right, left);
+}
+__device__ __forceinline__ float iou_center(const float4 a, const float4 b) {
+    const float w = overlap_c(a.x, a.z, b.x, b.z);
+    const float h = overlap_c(a.y, a.w, b.y, b.w);
+    const float inter = (w < 0.f || h < 0.f) ? 0.f : __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+struct KerasParams {
+    const float *heads[3];
+    int lh[3], lw[3], loff[4];
+    int n_layers, A, C, nbox, P;
+    float anchors[48];
+    float in_h, in_w;
+    float obj, iou;
+    int maxk;
+    const float *image_hw;
+    k2y_det *dets;
+    int *counts;
+    float4 *boxes;              // [B][nbox]
+    float *scores;              // [B][C][nbox]
+    unsigned long long *keys;   // [B][C][P]
+};
+
+// Collects the candidates of one class (score passes `pred`) in index order, sorts them.
+// Returns n; on return either `rkey` holds the sorted keys (n <= 32) or keys[0..n) does.
+template <bool GE>
+__device__ __forceinline__ int gather_sorted(const float *sc, int nbox, float thr, unsigned long long *keys, int lane,
+                                             unsigned long long &rkey) {
+    int n = 0;
+    for (int base = 0; base < nbox; base += 32) {
+        const int i = base + lane;
+        const float s = (i < nbox) ? sc[i] : -1.f;
+        const bool pass = (i < nbox) && (GE ? (s >= thr) : (s > thr));
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (pass) keys[n + __popc(m & ((1u << lane) - 1u))] = pack_key(s, i);
+        n += __popc(m);
+    }
+    __syncwarp();
+    rkey = 0ull;
+    if (n <= 32) {
+        if (lane < n) rkey = keys[lane];
+        rkey = warp_sort_desc(rkey, lane);
+    } else {
+        int P = 64;
+        while (P < n) P <<= 1;
+        for (int i = n + lane; i < P; i += 32) keys[i] = 0ull;
+        __syncwarp();
+        warp_sort_desc_mem(keys, P, lane);
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(DET_THREADS) detect_keras_kernel(const KerasParams p) {
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int E = 5 + p.C;
+    float4 *boxes = p.boxes + (size_t)b * p.nbox;
+    float *scores = p.scores + (size_t)b * p.C * p.nbox;
+
+    // correct_box constants for this image (keras_inference.py:53-58), float32, same op order.
+    const float img_h = p.image_hw[2 * b], img_w = p.image_hw[2 * b + 1];
+    const float r = fminf(__fdiv_rn(p.in_h, img_h), __fdiv_rn(p.in_w, img_w));
+    const float new_h = rintf(__fmul_rn(img_h, r)), new_w = rintf(__fmul_rn(img_w, r));
+    const float off_y = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_h, new_h), 2.0f), p.in_h);
+    const float off_x = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_w, new_w), 2.0f), p.in_w);
+    const float sc_y = __fdiv_rn(p.in_h, new_h), sc_x = __fdiv_rn(p.in_w, new_w);
+
+    // ---- phase 1: decode ----
+    for (int box = tid; box < p.nbox; box += DET_THREADS) {
+        int l = 0;
+        if (p.n_layers > 1 && box >= p.loff[1]) l = 1;
+        if (p.n_layers > 2 && box >= p.loff[2]) l = 2;
+        const int local = box - p.loff[l];
+        const int a = local % p.A;
+        const int cell = local / p.A;
+        const int W = p.lw[l], H = p.lh[l];
+        const int col = cell % W, row = cell / W;
+        const float *e = p.heads[l] + ((size_t)((size_t)b * H * W + cell) * p.A + a) * E;
+        const float tx = __ldg(e), ty = __ldg(e + 1), tw = __ldg(e + 2), th = __ldg(e + 3), tc = __ldg(e + 4);
+        // tf_xywh_to_all (tools/utils.py:545-546)
+        const float x = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)W);
+        const float y = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)H);
+        const float w = __fmul_rn(expf(tw), p.anchors[(l * p.A + a) * 2]);
+        const float h = __fmul_rn(expf(th), p.anchors[(l * p.A + a) * 2 + 1]);
+        // correct_box (keras_inference.py:59-71)
+        const float cy = __fmul_rn(__fsub_rn(y, off_y), sc_y), cx = __fmul_rn(__fsub_rn(x, off_x), sc_x);
+        const float hh = __fmul_rn(h, sc_y), ww = __fmul_rn(w, sc_x);
+        const float hh2 = __fdiv_rn(hh, 2.0f), ww2 = __fdiv_rn(ww, 2.0f);
+        float4 bx;
+        bx.x = __fmul_rn(__fsub_rn(cy, hh2), img_h);
+        bx.y = __fmul_rn(__fsub_rn(cx, ww2), img_w);
+        bx.z = __fmul_rn(__fadd_rn(cy, hh2), img_h);
+        bx.w = __fmul_rn(__fadd_rn(cx, ww2), img_w);
+        boxes[box] = bx;
+        const float sconf = sigmoidf_ref(tc);
+        for (int c = 0; c < p.C; ++c) scores[(size_t)c * p.nbox + box] = __fmul_rn(sigmoidf_ref(__ldg(e + 5 + c)), sconf);
+    }
+    __syncthreads();
+
+    // ---- phase 2: per-class NMS, one warp per class ----
+    const int warp = tid >> 5, lane = tid & 31, nwarps = DET_THREADS >> 5;
+    for (int c = warp; c < p.C; c += nwarps) {
+        unsigned long long *keys = p.keys + ((size_t)b * p.C + c) * p.P;
+        unsigned long long rkey;
+        const int n = gather_sorted<true>(scores + (size_t)c * p.nbox, p.nbox, p.obj, keys, lane, rkey);
+        k2y_det *out = p.dets + ((size_t)b * p.C + c) * p.maxk;
+        float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f);
+        int nsel = 0;
+        for (int i = 0; i < n && nsel < p.maxk; ++i) {
+            const unsigned long long key = (n <= 32) ? __shfl_sync(FULL, rkey, i) : keys[i];
+            const int idx = key_index(key);
+            const float4 cb = boxes[idx];
+            bool sup = (lane < nsel) && (iou_yxyx(cb, mybox) > p.iou);  // first 32 kept boxes live in registers
+            bool any = __ballot_sync(FULL, sup) != 0u;
+            for (int base = 32; !any && base < nsel; base += 32) {  // only when max_per_class > 32
+                const int j = base + lane;
+                sup = false;
+                if (j < nsel) {
+                    const k2y_det d = out[j];
+                    sup = iou_yxyx(cb, make_float4(d.ymin, d.xmin, d.ymax, d.xmax)) > p.iou;
+                }
+                any = __ballot_sync(FULL, sup) != 0u;
+            }
+            if (!any) {
+                if (lane == nsel) mybox = cb;
+                if (lane == 0) {
+                    k2y_det d;
+                    d.ymin = cb.x;
+                    d.xmin = cb.y;
+                    d.ymax = cb.z;
+                    d.xmax = cb.w;
+                    d.score = key_score(key);
+                    d.index = idx;
+                    out[nsel] = d;
+                }
+                ++nsel;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) p.counts[b * p.C + c] = nsel;
+    }
+}
+
+struct RegionParams {
+    const float *in;
+    float *out;                 // may be null
+    float *probs;               // [B][N][C+1]
+    float4 *boxes;              // [B][N]
+    float *scores;              // ws [B][C][N]
+    unsigned long long *keys;   // ws [B][C][P]
+    int *kept;                  // ws [B][C][N]
+    int W, H, A, C, N, P;
+    float anchors[16];
+    float thr, nms;
+    double dx, dy, sxw, syh;    // correct_region_boxes constants (region_layer.c:158-159)
+    float wscale, hscale;       // (:160-161)
+};
+
+__global__ void __launch_bounds__(DET_THREADS) region_kernel(const RegionParams p) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int wh = p.W * p.H, E = 5 + p.C;
+    const float *in = p.in + (size_t)b * p.A * E * wh;
+    float *outp = p.out ? p.out + (size_t)b * p.A * E * wh : nullptr;
+    float *probs = p.probs + (size_t)b * p.N * (p.C + 1);
+    float4 *boxes = p.boxes + (size_t)b * p.N;
+    float *scores = p.scores + (size_t)b * p.C * p.N;
+
+    // ---- phase 1: forward_region_layer + get_region_boxes + correct_region_boxes ----
+    for (int index = tid; index < p.N; index += DET_THREADS) {
+        const int a = index / wh, loc = index - a * wh;
+        const int row = loc / p.W, col = loc - row * p.W;
+        const float *e = in + (size_t)a * E * wh + loc;
+        const float sx = sigmoidf_ref(__ldg(e)), sy = sigmoidf_ref(__ldg(e + wh));
+        const float tw = __ldg(e + 2 * wh), th = __ldg(e + 3 * wh);
+        const float conf = sigmoidf_ref(__ldg(e + 4 * wh));
+        float largest = __ldg(e + 5 * wh);
+        for (int j = 1; j < p.C; ++j) largest = fmaxf(largest, __ldg(e + (5 + j) * wh));
+        float sum = 0.f;
+        for (int j = 0; j < p.C; ++j) sum = __fadd_rn(sum, expf(__fsub_rn(__ldg(e + (5 + j) * wh), largest)));
+        float mx = 0.f;
+        for (int j = 0; j < p.C; ++j) {
+            const float sm = __fdiv_rn(expf(__fsub_rn(__ldg(e + (5 + j) * wh), largest)), sum);
+            const float prob = __fmul_rn(conf, sm);
+            const float kept = (prob > p.thr) ? prob : 0.f;
+            probs[(size_t)index * (p.C + 1) + j] = kept;
+            scores[(size_t)j * p.N + index] = kept;
+            if (prob > mx) mx = prob;
+            if (outp) outp[(size_t)a * E * wh + (5 + j) * wh + loc] = sm;
+        }
+        probs[(size_t)index * (p.C + 1) + p.C] = mx;
+        if (outp) {
+            float *o = outp + (size_t)a * E * wh + loc;
+            o[0] = sx;
+            o[wh] = sy;
+            o[2 * wh] = tw;
+            o[3 * wh] = th;
+            o[4 * wh] = conf;
+        }
+        const float bx = __fdiv_rn(__fadd_rn((float)col, sx), (float)p.W);
+        const float by = __fdiv_rn(__fadd_rn((float)row, sy), (float)p.H);
+        const float bw = __fmul_rn(expf(tw), p.anchors[2 * a]);
+        const float bh = __fmul_rn(expf(th), p.anchors[2 * a + 1]);
+        float4 bb;
+        bb.x = (float)__ddiv_rn(__dsub_rn((double)bx, p.dx), p.sxw);
+        bb.y = (float)__ddiv_rn(__dsub_rn((double)by, p.dy), p.syh);
+        bb.z = __fmul_rn(bw, p.wscale);
+        bb.w = __fmul_rn(bh, p.hscale);
+        boxes[index] = bb;
+    }
+    __syncthreads();
+
+    // ---- phase 2: do_nms_sort, one warp per class, no output cap ----
+    const int warp = tid >> 5, lane = tid & 31, nwarps = DET_THREADS >> 5;
+    for (int k = warp; k < p.C; k += nwarps) {
+        unsigned long long *keys = p.keys + ((size_t)b * p.C + k) * p.P;
+        int *kept = p.kept + ((size_t)b * p.C + k) * p.N;
+        unsigned long long rkey;
+        const int n = gather_sorted<false>(scores + (size_t)k * p.N, p.N, 0.f, keys, lane, rkey);
+        float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f);
+        int nsel = 0;
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long key = (n <= 32) ? __shfl_sync(FULL, rkey, i) : keys[i];
+            const int idx = key_index(key);
+            const float4 cb = boxes[idx];
+            // box_iou(a = kept, b = candidate) — argument order as in the reference loop
+            bool sup = (lane < nsel) && (iou_center(mybox, cb) > p.nms);
+            bool any = __ballot_sync(FULL, sup) != 0u;
+            for (int base = 32; !any && base < nsel; base += 32) {
+                const int j = base + lane;
+                sup = (j < nsel) && (iou_center(boxes[kept[j]], cb) > p.nms);
+                any = __ballot_sync(FULL, sup) != 0u;
+            }
+            if (any) {
+                if (lane == 0) probs[(size_t)idx * (p.C + 1) + k] = 0.f;
+            } else {
+                if (lane == nsel) mybox = cb;
+                if (lane == 0) kept[nsel] = idx;
+                ++nsel;
+                __syncwarp();
+            }
+        }
+    }
+}
+
+inline int next_pow2(int v) {
+    int p = 64;
+    while (p < v) p <<= 1;
+    return p;
+}
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+}  // namespace k2y
+
+using namespace k2y;
+
+extern "C" int k2y_detect_workspace_bytes(const k2y_detect_cfg *cfg, int batch, size_t *bytes) {
+    if (!cfg || !bytes || batch <= 0 || cfg->n_layers < 1 || cfg->n_layers > 3) {
+        set_error("k2y_detect_workspace_bytes: bad arguments");
+        return K2Y_ERR_INVALID;
+    }
+    size_t nbox = 0;
+    for (int l = 0; l < cfg->n_layers; ++l) nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
+    const size_t P = next_pow2((int)nbox);
+    *bytes = align256((size_t)batch * nbox * sizeof(float4)) + align256((size_t)batch * cfg->class_num * nbox * sizeof(float)) +
+             align256((size_t)batch * cfg->class_num * P * sizeof(unsigned long long));
+    return K2Y_OK;
+}
+
+extern "C" int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *heads_dev, int batch,
+                                const float *image_hw_dev, k2y_det *dets_dev, int32_t *counts_dev, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    size_t need = 0;
+    int rc = k2y_detect_workspace_bytes(cfg, batch, &need);
+    if (rc != K2Y_OK) return rc;
+    if (!heads_dev || !image_hw_dev || !dets_dev || !counts_dev || !workspace || workspace_bytes < need) {
+        set_error("k2y_detect_keras: null pointer or workspace too small (%zu < %zu)", workspace_bytes, need);
+        return K2Y_ERR_INVALID;
+    }
+    if (cfg->anchor_num < 1 || cfg->anchor_num > 8 || cfg->class_num < 1 || cfg->max_per_class < 1) {
+        set_error("k2y_detect_keras: anchor_num must be 1..8, class_num and max_per_class >= 1");
+        return K2Y_ERR_INVALID;
+    }
+    KerasParams p;
+    p.n_layers = cfg->n_layers;
+    p.A = cfg->anchor_num;
+    p.C = cfg->class_num;
+    int off = 0;
+    for (int l = 0; l < 3; ++l) {
+        p.heads[l] = l < cfg->n_layers ? heads_dev[l] : nullptr;
+        p.lh[l] = l < cfg->n_layers ? cfg->layer_h[l] : 0;
+        p.lw[l] = l < cfg->n_layers ? cfg->layer_w[l] : 0;
+        p.loff[l] = off;
+        off += p.lh[l] * p.lw[l] * p.A;
+    }
+    p.loff[3] = off;
+    p.nbox = off;
+    p.P = next_pow2(off);
+    for (int i = 0; i < 48; ++i) p.anchors[i] = 0.f;
+    for (int i = 0; i < cfg->n_layers * cfg->anchor_num * 2; ++i) p.anchors[i] = cfg->anchors[i];
+    p.in_h = (float)cfg->in_h;
+    p.in_w = (float)cfg->in_w;
+    p.obj = cfg->obj_thresh;
+    p.iou = cfg->iou_thresh;
+    p.maxk = cfg->max_per_class;
+    p.image_hw = image_hw_dev;
+    p.dets = dets_dev;
+    p.counts = counts_dev;
+    char *ws = (char *)workspace;
+    p.boxes = (float4 *)ws;
+    ws += align256((size_t)batch * p.nbox * sizeof(float4));
+    p.scores = (float *)ws;
+    ws += align256((size_t)batch * p.C * p.nbox * sizeof(float));
+    p.keys = (unsigned long long *)ws;
+    detect_keras_kernel<<<batch, DET_THREADS, 0, (cudaStream_t)stream>>>(p);
+    K2Y_CUDA_CHECK(cudaGetLastError());
+    return K2Y_OK;
+}
+
+extern "C" int k2y_region_workspace_bytes(const k2y_region_cfg *cfg, int batch, size_t *bytes) {
+    if (!cfg || !bytes || batch <= 0) {
+        set_error("k2y_region_workspace_bytes: bad arguments");
+        return K2Y_ERR_INVALID;
+    }
+    const size_t N = (size_t)cfg->layer_w * cfg->layer_h * cfg->anchor_num;
+    const size_t P = next_pow2((int)N);
+    *bytes = align256((size_t)batch * cfg->classes * N * sizeof(float)) +
+             align256((size_t)batch * cfg->classes * P * sizeof(unsigned long long)) +
+             align256((size_t)batch * cfg->classes * N * sizeof(int));
+    return K2Y_OK;
+}
+
+extern "C" int k2y_region_run(const k2y_region_cfg *cfg, const float *in_dev, int batch, float *out_dev,
+                              float *probs_dev, float *boxes_dev, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    size_t need = 0;
+    int rc = k2y_region_workspace_bytes(cfg, batch, &need);
+    if (rc != K2Y_OK) return rc;
+    if (!in_dev || !probs_dev || !boxes_dev || !workspace || workspace_bytes < need) {
+        set_error("k2y_region_run: null pointer or workspace too small (%zu < %zu)", workspace_bytes, need);
+        return K2Y_ERR_INVALID;
+    }
+    if (cfg->anchor_num < 1 || cfg->anchor_num > 8 || cfg->classes < 1) {
+        set_error("k2y_region_run: anchor_num must be 1..8 and classes >= 1");
+        return K2Y_ERR_INVALID;
+    }
+    RegionParams p;
+    p.in = in_dev;
+    p.out = out_dev;
+    p.probs = probs_dev;
+    p.boxes = (float4 *)boxes_dev;
+    p.W = cfg->layer_w;
+    p.H = cfg->layer_h;
+    p.A = cfg->anchor_num;
+    p.C = cfg->classes;
+    p.N = p.W * p.H * p.A;
+    p.P = next_pow2(p.N);
+    for (int i = 0; i < 16; ++i) p.anchors[i] = i < 2 * p.A ? cfg->anchors[i] : 0.f;
+    p.thr = cfg->threshold;
+    p.nms = cfg->nms_value;
+    // correct_region_boxes (region_layer.c:139-164) — same C types and evaluation order.
+    {
+        const uint32_t net_width = (uint32_t)cfg->net_w, net_height = (uint32_t)cfg->net_h;
+        const uint32_t image_width = (uint32_t)cfg->image_w, image_height = (uint32_t)cfg->image_h;
+        int new_w = 0, new_h = 0;
+        if (((float)net_width / image_width) < ((float)net_height / image_height)) {
+            new_w = (int)net_width;
+            new_h = (int)((image_height * net_width) / image_width);
+        } else {
+            new_h = (int)net_height;
+            new_w = (int)((image_width * net_height) / image_height);
+        }
+        p.dx = (net_width - new_w) / 2. / net_width;
+        p.dy = (net_height - new_h) / 2. / net_height;
+        p.sxw = (double)((float)new_w / net_width);
+        p.syh = (double)((float)new_h / net_height);
+        p.wscale = (float)net_width / new_w;
+        p.hscale = (float)net_height / new_h;
+    }
+    char *ws = (char *)workspace;
+    p.scores = (float *)ws;
+    ws += align256((size_t)batch * p.C * p.N * sizeof(float));
+    p.keys = (unsigned long long *)ws;
+    ws += align256((size_t)batch * p.C * p.P * sizeof(unsigned long long));
+    p.kept = (int *)ws;
+    region_kernel<<<batch, DET_THREADS, 0, (cudaStream_t)stream>>>(p);
+    K2Y_CUDA_CHECK(cudaGetLastError());
+    return K2Y_OK;
+}

@@ -1,0 +1,63 @@
+"""Generates the committed golden fixtures from the reference's shipped assets.
+
+Run once in the build container (``python tests/golden/make_golden.py``); needs
+/root/reference, which does not exist on the GPU box — hence the committed outputs.
+
+Inputs (reference fixtures):
+  asset/yolo_model.h5   trained yolo_mobilev1 alpha=0.75, VOC-20   -> weights npz (same f32 values)
+  data/dog.jpg, data/people.jpg                                    -> decoded uint8 RGB arrays
+  data/voc_anchor.npy                                              -> copied values
+Outputs of the oracle / compiled reference on them:
+  dog_heads_f32.npz     oracle fp32 head tensors (TF-CPU stand-in) and fp64 ground truth
+  dog_golden.json       KERAS-dialect detections (obj 0.7, iou 0.5) + REGION_C draw list from the
+                        *compiled reference* region_layer.c (thr 0.6, nms 0.3 — main.c:280-287)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from k210_yolo_framework_b200.hdf5_min import load_keras_weights  # noqa: E402
+from oracle import decode_ref, keras_ref, region_c  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    w = load_keras_weights(f"{REF}/asset/yolo_model.h5")
+    flat = {f"{layer}/{var}": arr for layer, vs in w.items() for var, arr in vs.items()}
+    np.savez_compressed(f"{OUT}/yolo_mobilev1_075_voc_weights.npz", **flat)
+    anchors = np.load(f"{REF}/data/voc_anchor.npy")
+    np.save(f"{OUT}/voc_anchor.npy", anchors)
+    for name in ("dog", "people"):
+        img = np.array(Image.open(f"{REF}/data/{name}.jpg").convert("RGB"))
+        np.save(f"{OUT}/{name}_u8.npy", img)
+    dog = np.load(f"{OUT}/dog_u8.npy")
+    x = (dog / np.max(dog)).astype(np.float32)[None]
+    heads32 = keras_ref.forward("yolo_mobilev1", w, x, alpha=0.75)
+    heads64 = keras_ref.forward("yolo_mobilev1", w, x.astype(np.float64), alpha=0.75, dtype=torch.float64)
+    np.savez_compressed(f"{OUT}/dog_heads.npz", l0_f32=heads32[0], l1_f32=heads32[1],
+                        l0_f64=heads64[0], l1_f64=heads64[1])
+    h = decode_ref.HelperRef(anchors, [224, 320], [7, 10, 14, 20], 20)
+    yp = [hd[0].reshape(hd.shape[1], hd.shape[2], 3, 25) for hd in heads32]
+    det = decode_ref.detect_image(yp, h, [224, 320], dog.shape[:2], 0.7, 0.5)
+    gold = {"keras": {"obj_thresh": 0.7, "iou_thresh": 0.5,
+                      "detections": [[int(d[0]), int(d[1])] + [float(v) for v in d[2:]] for d in det]},
+            "region_c": {"threshold": 0.6, "nms_value": 0.3, "layers": []}}
+    for l, (W, H) in enumerate([(10, 7), (20, 14)]):
+        chw = region_c.nhwc_to_chw(heads32[l][0], 3)
+        r = region_c.RegionLayerRef(W, H, 75, 320, 224, anchors[l].reshape(-1), 0.6, 0.3)
+        gold["region_c"]["layers"].append([[int(v) for v in t[:5]] + [float(t[5])] for t in r.run(chw)])
+    with open(f"{OUT}/dog_golden.json", "w") as fh:
+        json.dump(gold, fh, indent=1)
+    print(json.dumps(gold, indent=1))
+
+
+if __name__ == "__main__":
+    main()
