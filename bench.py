@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the YOLOv3 inference hot path (BASELINE.json metric: images/sec, yolo_mobilev1-0.75 @320x224).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch of 32 synthetic images per GPU: network forward (one CUDA
+graph) + fused decode/NMS (+ one all-gather of the detection records when N > 1).  Weak scaling: the per-GPU
+batch is fixed, `value` is the whole-job images/sec = N*32*K / (max over ranks of the summed per-step device
+times).  Prints ONE JSON line (rank 0).
+
+  value      inputs resident in HBM, per-step CUDA events on the launching stream, L2 flushed between steps
+  e2e        same metric through DetectionPipeline.detect_host(): pinned-host input -> H2D -> step -> D2H records
+  roofline   dominant kernel of the step, timed live with CUDA events (k2y_net_profile), vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle ("port" of the reference TF-CPU path: torch-CPU fp32 convs + numpy NMS) on the host cores
+
+`--impl reference` times that CPU path alone (TensorFlow 1.14 cannot be installed offline; the stand-in is
+labelled as such) and prints the same JSON shape with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL_DEF, ALPHA, IN_HW, CLASSES, BATCH = "yolo_mobilev1", 0.75, (224, 320), 20, 32
+OBJ_THRESH, IOU_THRESH = 0.7, 0.5
+WORKLOAD = "cfg2: yolo_mobilev1 a=0.75, 320x224 (HxW 224x320), batch 32/GPU, VOC-20 anchors, random-init detection-rich weights (seed 0)"
+FLOP_PER_IMAGE = 1.465e9
+METRIC = "images/sec @320x224 yolo_mobilev1-0.75"
+
+
+def anchors():
+    return np.load(os.path.join(ROOT, "tests", "golden", "voc_anchor.npy"))
+
+
+def bench_weights(expected):
+    from k210_yolo_framework_b200.weights import random_weights
+    return random_weights(expected, seed=0, detection_rich=True, head_bias=-0.2, head_bias_std=1.5)
+
+
+def synthetic_batch(seed, n=BATCH):
+    return np.random.default_rng(seed).random((n, IN_HW[0], IN_HW[1], 3), dtype=np.float32)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_throughput(budget_s=15.0, min_reps=2):
+    """The reference's CPU path (TF-CPU stand-in: oracle torch-CPU convs + numpy NMS), all host threads."""
+    import torch
+    from oracle import decode_ref, keras_ref
+    from k210_yolo_framework_b200 import yolonet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    m, _ = yolonet.yolo_mobilev1([IN_HW[0], IN_HW[1], 3], 3, CLASSES, alpha=ALPHA, max_batch=1)  # host-side graph only (names/shapes)
+    w = bench_weights(m.engine.expected_variables())
+    h = decode_ref.HelperRef(anchors(), list(IN_HW), [(IN_HW[0] // 32, IN_HW[1] // 32), (IN_HW[0] // 16, IN_HW[1] // 16)], CLASSES)
+    x = synthetic_batch(100)
+    shapes = [IN_HW] * BATCH
+
+    cache = {}
+
+    def one():
+        heads = keras_ref.forward(MODEL_DEF, w, x, alpha=ALPHA, cache=cache, channels_last=True)
+        return decode_ref.detect_batch_fast(heads, h, list(IN_HW), shapes, OBJ_THRESH, IOU_THRESH)
+    one()  # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    ips = BATCH / float(np.median(times))
+    return ips, threads, f"{len(times)} x batch {BATCH} of the bench workload, forward + decode + NMS, median"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each step = one bounded sample (a batch of 32); steps/warmup as requested
+    import torch
+    from oracle import decode_ref, keras_ref
+    from k210_yolo_framework_b200 import yolonet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    m, _ = yolonet.yolo_mobilev1([IN_HW[0], IN_HW[1], 3], 3, CLASSES, alpha=ALPHA, max_batch=1)
+    w = bench_weights(m.engine.expected_variables())
+    h = decode_ref.HelperRef(anchors(), list(IN_HW), [(7, 10), (14, 20)], CLASSES)
+    x = synthetic_batch(100)
+    shapes = [IN_HW] * BATCH
+
+    cache = {}
+
+    def one():
+        heads = keras_ref.forward(MODEL_DEF, w, x, alpha=ALPHA, cache=cache, channels_last=True)
+        return decode_ref.detect_batch_fast(heads, h, list(IN_HW), shapes, OBJ_THRESH, IOU_THRESH)
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    ips = BATCH * args.steps / dt
+    sample = f"{args.steps} steps x batch {BATCH}; TF-CPU stand-in (TF 1.14 unavailable offline): oracle torch-CPU (oneDNN, channels_last) fp32 convs + numpy NMS"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH, "note": "CPU only; one process on rank 0"},
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from k210_yolo_framework_b200 import _lib
+    from k210_yolo_framework_b200.pipeline import DetectionPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    math_mode = {"fp32_simt": _lib.MATH_FP32_SIMT, "tc_3xtf32": _lib.MATH_TC_3XTF32, "tc_tf32": _lib.MATH_TC_TF32}[args.math]
+
+    pipe = DetectionPipeline(MODEL_DEF, IN_HW, anchors(), CLASSES, ALPHA, BATCH, OBJ_THRESH, IOU_THRESH, 30, device=local,
+                             world=world, rank=rank)
+    pipe.engine.set_weights(bench_weights(pipe.engine.expected_variables()))
+    pipe.engine.set_math(math_mode)
+    x_host = torch.from_numpy(synthetic_batch(1000 + rank)).pin_memory()
+    pipe.engine.input_buffer.copy_(x_host)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        pipe.step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                       # L2 flush, outside the timed window of the step
+        starts[i].record(stream)
+        pipe.step_device()
+        ends[i].record(stream)
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+
+    # ---- end to end: pinned host input -> H2D -> step -> D2H records ----------------------------
+    for _ in range(2):
+        pipe.detect_host(x_host)
+    barrier()
+    t_e2e = 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hd, hc = pipe.detect_host(x_host)   # returns after the stream synchronise
+        t_e2e += time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    n_found = int(hc.sum())
+
+    t = torch.tensor([dev_ms, t_e2e * 1000.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = load_peaks()
+        # dominant kernel, timed live with CUDA events between launches (k2y_net_profile), L2 flushed before each pass
+        acc = None
+        reps = 5
+        for _ in range(reps):
+            flush.zero_()
+            prof = pipe.engine.profile(BATCH)
+            acc = prof if acc is None else [dict(a, ms=a["ms"] + b["ms"]) for a, b in zip(acc, prof)]
+        for a in acc:
+            a["ms"] /= reps
+        net_ms = sum(a["ms"] for a in acc)
+        top = max(acc, key=lambda a: a["ms"])
+        tf32_note = "tensor peak = measured dense bf16 (cuBLAS); a tf32 kernel tops out at 1/2 of it, 3xTF32 at 1/6"
+        roof = {"kernel": top["name"], "bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "traffic": None, "peak_source": peaks["source"],
+                "launch_ms": top["ms"], "share_of_net": top["ms"] / net_ms, "note": tf32_note}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        layer_roof = sum(max(a["flops"] / (peaks["bf16_tflops"] * 1e12), a["bytes"] / (peaks["hbm_gbs"] * 1e9)) for a in acc) * 1e3
+        ms_per_step = dev_ms / args.steps
+        value = world * BATCH * args.steps / (dev_ms * 1e-3)
+        cpu_ips, cores, sample = cpu_reference_throughput() if not args.no_cpu else (None, 0, "skipped")
+        out = {
+            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32_simt": "f32", "tc_3xtf32": "tf32x3 (fp32 storage, fp32 accumulate)", "tc_tf32": "tf32"}[args.math],
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "math": args.math, "parallelism": f"image-shard x{world}",
+                       "l2": "flushed between steps (256 MiB write outside the per-step event window)",
+                       "detections_per_step": n_found, "obj_thresh": OBJ_THRESH, "iou_thresh": IOU_THRESH},
+            "e2e": {"value": world * BATCH * args.steps / (e2e_ms * 1e-3), "unit": "images/sec",
+                    "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(hd.numel() * 4 + hc.numel() * 4),
+                    "api": "DetectionPipeline.detect_host (pinned host f32 NHWC in, detection records out)"},
+            "gpu_launches": pipe.launches_per_step() * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "conv_roofline": {"layerwise_floor_ms": layer_roof, "net_ms_event_sum": net_ms, "frac": layer_roof / net_ms,
+                              "tensor_frac_whole_net": BATCH * FLOP_PER_IMAGE / (net_ms * 1e-3) / (peaks["bf16_tflops"] * 1e12),
+                              "note": "sum over layers of max(FLOP/peak_bf16, fp32 act bytes/peak_hbm) / measured sum of launches"},
+            "cpu_baseline": {"value": cpu_ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample,
+                             "label": "TF-CPU stand-in (TF unavailable offline)"},
+            "top_launches": sorted(({"name": a["name"], "ms": round(a["ms"], 4)} for a in acc), key=lambda a: -a["ms"])[:6],
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--math", choices=["fp32_simt", "tc_3xtf32", "tc_tf32"], default=os.environ.get("K2Y_BENCH_MATH", "fp32_simt"))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -382,7 +382,9 @@ int check_net(const k2y_net *n, const char *fn) {
     return K2Y_OK;
 }
 
-int issue_layers(k2y_net *n, int batch, cudaStream_t st) {
+int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullptr) {
+    int li = 0;
+    if (ev) cudaEventRecord(ev[0], st);
     for (Layer &L : n->layers) {
         const Tensor &s0 = n->tensors[L.src0];
         const Tensor &d = n->tensors[L.dst];
@@ -453,6 +455,8 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st) {
             set_error("layer %s: launch failed: %s", L.name.c_str(), cudaGetErrorString(e));
             return K2Y_ERR_CUDA;
         }
+        ++li;
+        if (ev) cudaEventRecord(ev[li], st);
     }
     return K2Y_OK;
 }
@@ -841,4 +845,53 @@ extern "C" int k2y_net_read_layer(k2y_net *net, const char *name, int batch, flo
     }
     set_error("k2y_net_read_layer: no layer named '%s'", name);
     return K2Y_ERR_INVALID;
+}
+
+extern "C" int k2y_net_profile(k2y_net *net, int batch, void *stream, float *ms_per_launch, int n) {
+    if (check_net(net, "k2y_net_profile") || !ms_per_launch) return K2Y_ERR_INVALID;
+    if (!net->finalized || !net->bound) {
+        set_error("k2y_net_profile: net must be finalized and bound first");
+        return K2Y_ERR_STATE;
+    }
+    const int L = (int)net->layers.size();
+    if (n < L || batch <= 0 || batch > net->max_batch) {
+        set_error("k2y_net_profile: need room for %d launches, batch 1..%d", L, net->max_batch);
+        return K2Y_ERR_INVALID;
+    }
+    std::vector<cudaEvent_t> ev(L + 1);
+    for (auto &e : ev) K2Y_CUDA_CHECK(cudaEventCreate(&e));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = issue_layers(net, batch, st, ev.data());
+    if (rc == K2Y_OK) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("k2y_net_profile: %s", cudaGetErrorString(e));
+            rc = K2Y_ERR_CUDA;
+        }
+    }
+    if (rc == K2Y_OK)
+        for (int i = 0; i < L; ++i) cudaEventElapsedTime(&ms_per_launch[i], ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+extern "C" int k2y_net_launch_info(const k2y_net *net, int i, char *name, int name_len, double *flops_per_image,
+                                   double *bytes_per_image) {
+    if (check_net(net, "k2y_net_launch_info") || i < 0 || i >= (int)net->layers.size()) {
+        set_error("k2y_net_launch_info: index out of range");
+        return K2Y_ERR_INVALID;
+    }
+    const Layer &L = net->layers[i];
+    const Tensor &d = net->tensors[L.dst];
+    if (name && name_len > 0) snprintf(name, name_len, "%s", L.name.c_str());
+    double in_elems = 0;
+    for (int s : {L.src0, L.src1, L.res})
+        if (s >= 0) in_elems += (double)net->tensors[s].h * net->tensors[s].w * net->tensors[s].c;
+    const double out_elems = (double)d.h * d.w * d.c;
+    double macs = 0;
+    if (L.kind == L_CONV) macs = out_elems * L.kh * L.kw * L.cin;
+    else if (L.kind == L_DW) macs = out_elems * 9;
+    if (flops_per_image) *flops_per_image = 2.0 * macs;
+    if (bytes_per_image) *bytes_per_image = 4.0 * (in_elems + out_elems);  // algorithmic: activations read once + written once
+    return K2Y_OK;
 }

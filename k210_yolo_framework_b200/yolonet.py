@@ -208,6 +208,21 @@ class YoloEngine:
             check(lib.k2y_net_predict_host(self._h, x[s:s + n].ctypes.data, n, ptrs, ctypes.c_void_p(st.cuda_stream)))
         return outs
 
+    def profile(self, batch: int) -> List[dict]:
+        """One event-instrumented pass: [{name, ms, flops, bytes}] per launch (flops/bytes for `batch` images)."""
+        self._bind()
+        n = self.launches_per_run()
+        ms = (ctypes.c_float * n)()
+        st = torch.cuda.current_stream(self.device_index)
+        check(lib.k2y_net_profile(self._h, int(batch), ctypes.c_void_p(st.cuda_stream), ms, n))
+        out = []
+        for i in range(n):
+            name = ctypes.create_string_buffer(64)
+            fl, by = ctypes.c_double(), ctypes.c_double()
+            check(lib.k2y_net_launch_info(self._h, i, name, 64, ctypes.byref(fl), ctypes.byref(by)))
+            out.append({"name": name.value.decode(), "ms": float(ms[i]), "flops": fl.value * batch, "bytes": by.value * batch})
+        return out
+
     def read_layer(self, name: str, batch: int) -> np.ndarray:
         """Parity hook: output of conv layer `name` from the last run (needs set_keep_all(True), no graph)."""
         buf = np.empty(batch * self.in_h * self.in_w * 32, np.float32)  # >= any layer output

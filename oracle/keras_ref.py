@@ -38,9 +38,10 @@ BN_EPS = 1e-3  # keras BatchNormalization default epsilon (h5 model_config: 0.00
 class _Tape:
     """Executes Keras-layer semantics eagerly and hands out Keras auto-names."""
 
-    def __init__(self, weights: Weights, dtype: torch.dtype, record: bool = False):
+    def __init__(self, weights: Weights, dtype: torch.dtype, record: bool = False, cache: dict = None):
         self.w = weights
         self.dtype = dtype
+        self.cache = cache  # optional {key: converted tensor} reused across calls (CPU-baseline timing)
         self._count: Dict[str, int] = {}
         self.record = record
         self.acts: Dict[str, torch.Tensor] = {}
@@ -62,11 +63,17 @@ class _Tape:
     def zero_pad(self, x, top, bottom, left, right):
         return F.pad(x, (left, right, top, bottom))
 
+    def _cached(self, key, make):
+        if self.cache is None:
+            return make()
+        if key not in self.cache:
+            self.cache[key] = make()
+        return self.cache[key]
+
     def conv(self, x, name, stride=1, padding="same", use_bias=False):
-        k = self._t(self.w[name]["kernel"])  # HWIO
-        kh = k.shape[0]
-        wt = k.permute(3, 2, 0, 1).contiguous()
-        b = self._t(self.w[name]["bias"]) if use_bias else None
+        kh = self.w[name]["kernel"].shape[0]  # HWIO
+        wt = self._cached((name, "w"), lambda: self._t(self.w[name]["kernel"]).permute(3, 2, 0, 1).contiguous())
+        b = self._cached((name, "b"), lambda: self._t(self.w[name]["bias"])) if use_bias else None
         if padding == "same":
             assert stride == 1, "the reference never uses SAME with stride 2 for convs"
             p = kh // 2
@@ -75,20 +82,21 @@ class _Tape:
         return self._rec(name, F.conv2d(x, wt, b, stride=stride, padding=p))
 
     def dwconv(self, x, name, stride=1, padding="same"):
-        k = self._t(self.w[name]["depthwise_kernel"])  # (3,3,C,1)
-        c = k.shape[2]
-        wt = k.permute(2, 3, 0, 1).contiguous()  # (C,1,3,3)
+        c = self.w[name]["depthwise_kernel"].shape[2]  # (3,3,C,1)
+        wt = self._cached((name, "w"), lambda: self._t(self.w[name]["depthwise_kernel"]).permute(2, 3, 0, 1).contiguous())  # (C,1,3,3)
         p = 1 if padding == "same" else 0
         if padding == "same":
             assert stride == 1
         return self._rec(name, F.conv2d(x, wt, None, stride=stride, padding=p, groups=c))
 
     def bn(self, x, name):
-        p = self.w[name]
-        g, b = self._t(p["gamma"]), self._t(p["beta"])
-        m, v = self._t(p["moving_mean"]), self._t(p["moving_variance"])
-        inv = torch.rsqrt(v + BN_EPS) * g
-        return self._rec(name, (x - m[None, :, None, None]) * inv[None, :, None, None] + b[None, :, None, None])
+        def make():
+            p = self.w[name]
+            g, b = self._t(p["gamma"]), self._t(p["beta"])
+            m, v = self._t(p["moving_mean"]), self._t(p["moving_variance"])
+            return m[None, :, None, None], (torch.rsqrt(v + BN_EPS) * g)[None, :, None, None], b[None, :, None, None]
+        m, inv, b = self._cached((name, "bn"), make)
+        return self._rec(name, (x - m) * inv + b)
 
     def leaky(self, x, alpha, name=None):
         a = float(np.float32(alpha))
@@ -271,13 +279,15 @@ def _make_last_layers(t: _Tape, x):
 # public entry: forward(model_def, weights, x_nhwc) -> list of [N,h,w,A*(5+C)]
 # ---------------------------------------------------------------------------
 def forward(model_def: str, weights: Weights, x_nhwc: np.ndarray, alpha: float = 1.0,
-            dtype: torch.dtype = torch.float32, record: bool = False):
+            dtype: torch.dtype = torch.float32, record: bool = False, cache: dict = None, channels_last: bool = False):
     """Run the plain ``yolo_model`` graph; returns NHWC head tensors ``[N,h_l,w_l,A*(5+C)]``.
 
     With ``record=True`` also returns ``{layer_name: NCHW tensor}`` of intermediate outputs.
     """
-    t = _Tape(weights, dtype, record)
+    t = _Tape(weights, dtype, record, cache)
     x = _to_nchw(x_nhwc, dtype)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
     with torch.no_grad():
         if model_def == "yolo_mobilev1":
             x1, x2 = _mobilenet_v1(t, x, alpha)

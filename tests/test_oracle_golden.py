@@ -99,3 +99,18 @@ def test_correct_box_letterbox_math():
     sx = 320 / new_w
     cx = (0.5 - (320 - new_w) / 2 / 320) * sx
     np.testing.assert_allclose(b[0], [(0.5 - 0.2) * 374, (cx - 0.1 * sx) * 499, (0.5 + 0.2) * 374, (cx + 0.1 * sx) * 499], rtol=1e-5)
+
+
+def test_fast_nms_equals_reference_nms():
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n = int(rng.integers(1, 120))
+        yx = rng.random((n, 2)) * 100
+        hw = rng.random((n, 2)) * 40
+        boxes = np.concatenate([yx, yx + hw], 1).astype(np.float32)
+        if trial % 4 == 0:
+            boxes[:, [0, 2]] = boxes[:, [2, 0]]          # un-normalised corners
+        scores = np.round(rng.random(n), 2).astype(np.float32)   # many ties
+        a = decode_ref.nms_tf(boxes, scores, 30, 0.4)
+        b = decode_ref.nms_tf_fast(boxes, scores, 30, 0.4)
+        assert a.tolist() == b.tolist()
