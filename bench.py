@@ -101,13 +101,43 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cpus():
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def tune_threads(fn, avail):
+    """Pick the torch intra-op thread count that runs `fn` fastest (more threads than the layer sizes can feed
+    only adds synchronisation cost) — the baseline gets its best configuration."""
+    import torch
+    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail} or {avail})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_throughput(budget_s=15.0, min_reps=2):
     """The reference's CPU path (TF-CPU stand-in: oracle torch-CPU convs + numpy NMS), all host threads."""
     import torch
     from oracle import decode_ref, keras_ref
     from k210_yolo_framework_b200 import yolonet
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    avail = usable_cpus()
     m, _ = yolonet.yolo_mobilev1([IN_HW[0], IN_HW[1], 3], 3, CLASSES, alpha=ALPHA, max_batch=1)  # host-side graph only (names/shapes)
     w = bench_weights(m.engine.expected_variables())
     h = decode_ref.HelperRef(anchors(), list(IN_HW), [(IN_HW[0] // 32, IN_HW[1] // 32), (IN_HW[0] // 16, IN_HW[1] // 16)], CLASSES)
@@ -119,7 +149,7 @@ def cpu_reference_throughput(budget_s=15.0, min_reps=2):
     def one():
         heads = keras_ref.forward(MODEL_DEF, w, x, alpha=ALPHA, cache=cache, channels_last=True)
         return decode_ref.detect_batch_fast(heads, h, list(IN_HW), shapes, OBJ_THRESH, IOU_THRESH)
-    one()  # warm-up
+    threads = tune_threads(one, avail)
     times = []
     t_end = time.perf_counter() + budget_s
     while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < 50):
@@ -127,7 +157,8 @@ def cpu_reference_throughput(budget_s=15.0, min_reps=2):
         one()
         times.append(time.perf_counter() - t0)
     ips = BATCH / float(np.median(times))
-    return ips, threads, f"{len(times)} x batch {BATCH} of the bench workload, forward + decode + NMS, median"
+    return ips, threads, (f"{len(times)} x batch {BATCH} of the bench workload, forward + decode + NMS, median; "
+                          f"{threads} torch threads (best of a sweep) of {avail} usable cores")
 
 
 def run_reference(args):
@@ -138,8 +169,7 @@ def run_reference(args):
     import torch
     from oracle import decode_ref, keras_ref
     from k210_yolo_framework_b200 import yolonet
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    avail = usable_cpus()
     m, _ = yolonet.yolo_mobilev1([IN_HW[0], IN_HW[1], 3], 3, CLASSES, alpha=ALPHA, max_batch=1)
     w = bench_weights(m.engine.expected_variables())
     h = decode_ref.HelperRef(anchors(), list(IN_HW), [(7, 10), (14, 20)], CLASSES)
@@ -151,6 +181,7 @@ def run_reference(args):
     def one():
         heads = keras_ref.forward(MODEL_DEF, w, x, alpha=ALPHA, cache=cache, channels_last=True)
         return decode_ref.detect_batch_fast(heads, h, list(IN_HW), shapes, OBJ_THRESH, IOU_THRESH)
+    threads = tune_threads(one, avail)
     for _ in range(args.warmup):
         one()
     t0 = time.perf_counter()
@@ -158,7 +189,7 @@ def run_reference(args):
         one()
     dt = time.perf_counter() - t0
     ips = BATCH * args.steps / dt
-    sample = f"{args.steps} steps x batch {BATCH}; TF-CPU stand-in (TF 1.14 unavailable offline): oracle torch-CPU (oneDNN, channels_last) fp32 convs + numpy NMS"
+    sample = f"{args.steps} steps x batch {BATCH}; TF-CPU stand-in (TF 1.14 unavailable offline): oracle torch-CPU (oneDNN, channels_last) fp32 convs + numpy NMS; {threads} torch threads (best of a sweep) of {avail} usable cores"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -103,6 +103,16 @@ int k2y_net_set_keep_all(k2y_net *net, int keep_all);
 int k2y_net_read_layer(k2y_net *net, const char *name, int batch, float *host, size_t host_floats, int *h,
                        int *w, int *c);
 
+/* Kernel-parity hook: ONE dense convolution (the op DarknetConv2D / Conv2D lower to) on device NHWC f32 tensors,
+ * synchronous.  kernel_host is Keras HWIO [k,k,c0+c1,cout]; y = act(conv(x) * scale + shift) (+ residual).
+ * The input is concat(src0 [optionally nearest-upsampled x2, stored at h/2 x w/2], src1).  pad_mode: 0 = SAME
+ * (stride 1), 1 = ZeroPadding2D((1,1),(1,1)) + VALID, 2 = ZeroPadding2D((1,0),(1,0)) + VALID.  act: 0 none,
+ * 1 leaky(alpha), 2 relu, 3 relu6. */
+int k2y_conv2d(const float *src0_dev, const float *src1_dev, const float *residual_dev, float *dst_dev,
+               const float *kernel_host, const float *scale_host, const float *shift_host, int batch, int h, int w,
+               int c0, int c1, int up0, int cout, int ksize, int stride, int pad_mode, int act, float alpha,
+               int math_mode, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * KERAS-dialect decode + per-class NMS  (keras_inference.py:94-135; tools/utils.py:524-547
  * tf_xywh_to_all; keras_inference.py:32-72 correct_box; tf.image.non_max_suppression).

@@ -74,6 +74,8 @@ _SIGNATURES = {
     "k2y_net_set_keep_all": (c_int, [c_void_p, c_int]),
     "k2y_net_read_layer": (c_int, [c_void_p, c_char_p, c_int, c_void_p, c_size_t, POINTER(c_int), POINTER(c_int),
                                    POINTER(c_int)]),
+    "k2y_conv2d": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 11 +
+                   [c_float, c_int, c_void_p]),
     "k2y_detect_workspace_bytes": (c_int, [POINTER(DetectCfg), c_int, POINTER(c_size_t)]),
     "k2y_detect_keras": (c_int, [POINTER(DetectCfg), POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),

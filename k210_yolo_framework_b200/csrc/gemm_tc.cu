@@ -1,10 +1,602 @@
-// Placeholder until the tcgen05 kernels land: reports "unsupported" so every layer runs on the
-// fp32 CUDA-core path.
+// tcgen05 tensor-core convolution for sm_100a: 1x1 and 3x3 dense convs as (implicit) GEMMs
+//   D[M,N] = A[M,K] * W[N,K]^T,  M = B*OH*OW pixels, K = kh*kw*Cin, N = Cout
+// with fp32 NHWC storage in HBM and tf32 MMA (fp32 accumulate in TMEM).
+//
+// One persistent, warp-specialised CTA per SM walks the (m-tile, n-tile) list:
+//   warp 0      TMA producer   weights (hi/lo planes) every k-block; the A tile too when the conv is a
+//                              plain 1x1 (A is then just the [M,K] row-major activation matrix)
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma kind::tf32 (M=128, N=BN, K=8),
+//                              accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 2-5   A gather       3x3 / strided / concat / nearest-upsample inputs: each thread owns one GEMM row
+//                              and cp.async's its 128-byte k-slice (zero-fill = padding) into the 128B-swizzled
+//                              K-major layout the UMMA descriptor expects  (only in the GATHER variant)
+//   warps 6-9   converter      3xTF32: split the landed fp32 A tile in place into hi = tf32(a) and
+//                              lo = tf32(a - hi) planes (the weights were split on the host), so that
+//                              hi*hi + lo*hi + hi*lo recovers fp32-class accuracy from tf32 tensor cores
+//   warps 10-13 epilogue       tcgen05.ld TMEM -> registers, folded-BN scale/shift, activation, residual, store
+// mbarrier pipelines: full_b (TMA tx) / full_a (cp.async) -> conv_done -> [MMA] -> empty (tcgen05.commit);
+// tmem_full (commit) -> [epilogue] -> tmem_empty.
+//
+// Replaces the TF Conv2D + FusedBatchNorm + LeakyRelu/Relu6 (+ ResizeNearestNeighbor/ConcatV2/Add) ops that
+// models/yolonet.py:244-260 and models/keras_mobilenet*.py compose; see DESIGN.md for the rooflines.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "gemm_tc.h"
 
 namespace k2y {
-int tc_pack(TcWeights &, const float *, int, int) { return K2Y_OK; }
-void tc_free(TcWeights &) {}
-bool tc_supported(const ConvArgs &, const TcWeights &) { return false; }
-cudaError_t launch_conv_tc(const ConvArgs &, const TcWeights &, int, cudaStream_t) { return cudaErrorNotSupported; }
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile (UMMA_M)
+constexpr int BK = 32;           // fp32 per k-block = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;        // tf32
+constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
+constexpr int NUM_THREADS = 14 * 32;
+constexpr int MAX_STAGES = 8;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t tx) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 in [0,14), LBO (ignored for swizzled K-major) in [16,30), SBO = 1024 B (one 8-row x 128 B
+// swizzle atom) in [32,46), version 1 in [46,48), layout type SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcParams {
+    // gather-mode A source (also used for the shape arithmetic in both modes)
+    const float *src0, *src1;
+    int H, W, C0, C1, up0;          // logical input extent (after upsampling src0)
+    int OH, OW, kh, kw, stride, pad_t, pad_l;
+    // epilogue
+    float *dst;
+    const float *residual, *scale, *shift;
+    int act;
+    float alpha;
+    int M, N, K;
+    int BN, n_tiles, m_tiles, nkb, stages;
+    int three_x;                    // 1 = 3xTF32, 0 = single pass
+    uint32_t tmem_cols;
+};
+
+struct __align__(8) Barriers {
+    uint64_t full_b[MAX_STAGES], full_a[MAX_STAGES], conv[MAX_STAGES], empty[MAX_STAGES];
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_slot;
+};
+
+template <bool GATHER>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+               const __grid_constant__ CUtensorMap map_blo, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages] x { A_hi(raw) 16K | A_lo 16K (3x) | B_hi BN*128 | B_lo BN*128 (3x) }, then barriers
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t stage_bytes = (uint32_t)A_TILE_BYTES * (p.three_x ? 2u : 1u) + b_bytes * (p.three_x ? 2u : 1u);
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_gen + (size_t)p.stages * stage_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool use_conv = p.three_x || GATHER;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&bars->full_b[s]), 1);
+            mbar_init(smem_u32(&bars->full_a[s]), 128);
+            mbar_init(smem_u32(&bars->conv[s]), 128);
+            mbar_init(smem_u32(&bars->empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&bars->tmem_full[a]), 1);
+            mbar_init(smem_u32(&bars->tmem_empty[a]), 128);
+        }
+        fence_barrier_init();
+        if (!GATHER) prefetch_tmap(&map_a);
+        prefetch_tmap(&map_bhi);
+        if (p.three_x) prefetch_tmap(&map_blo);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_slot), p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_slot;
+
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    auto stage_a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
+    auto stage_a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES; };
+    auto stage_b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES * (p.three_x ? 2u : 1u); };
+    auto stage_b_lo = [&](int s) { return stage_b_hi(s) + b_bytes; };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t tx = b_bytes * (p.three_x ? 2u : 1u) + (GATHER ? 0u : (uint32_t)A_TILE_BYTES);
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                    const uint32_t fb = smem_u32(&bars->full_b[s]);
+                    mbar_arrive_expect_tx(fb, tx);
+                    if (!GATHER) tma_load_2d(stage_a_hi(s), &map_a, fb, kb * BK, mt * BM);
+                    tma_load_2d(stage_b_hi(s), &map_bhi, fb, kb * BK, nt * p.BN);
+                    if (p.three_x) tma_load_2d(stage_b_lo(s), &map_blo, fb, kb * BK, nt * p.BN);
+                    if (++s == p.stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, p.BN);
+            int s = 0;
+            uint32_t ph = 0, acc_it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
+                const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                mbar_wait(smem_u32(&bars->tmem_empty[a]), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + a * (uint32_t)p.BN;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(smem_u32(&bars->full_b[s]), ph);
+                    if (use_conv) mbar_wait(smem_u32(&bars->conv[s]), ph);
+                    tc_fence_after();
+                    const uint64_t a_hi = make_desc_sw128(stage_a_hi(s)), b_hi = make_desc_sw128(stage_b_hi(s));
+                    const uint64_t a_lo = make_desc_sw128(stage_a_lo(s)), b_lo = make_desc_sw128(stage_b_lo(s));
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
+                        if (p.three_x) {
+                            // small terms first, then the dominant hi*hi
+                            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
+                            umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+                        } else {
+                            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+                        }
+                    }
+                    umma_commit(smem_u32(&bars->empty[s]));  // frees the smem slot when these MMAs retire
+                    if (++s == p.stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                umma_commit(smem_u32(&bars->tmem_full[a]));
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ================= A gather (implicit GEMM rows) =================
+        if (GATHER) {
+            const int r = threadIdx.x - 64;  // GEMM row inside the tile, 0..127
+            const int Cin = p.C0 + p.C1;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int mt = t / p.n_tiles;
+                const int m = mt * BM + r;
+                int b = -1, iy0 = 0, ix0 = 0;
+                if (m < p.M) {
+                    const int ox = m % p.OW;
+                    const int q = m / p.OW;
+                    const int oy = q % p.OH;
+                    b = q / p.OH;
+                    iy0 = oy * p.stride - p.pad_t;
+                    ix0 = ox * p.stride - p.pad_l;
+                }
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    // a k-block = 32 consecutive channels of ONE tap of ONE source (Cin % 32 == 0, C0 % 32 == 0)
+                    const int k = kb * BK;
+                    const int tap = k / Cin;
+                    const int ci = k - tap * Cin;
+                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                    const int iy = iy0 + ky, ix = ix0 + kx;
+                    const bool ok = b >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    const float *src = p.src0;
+                    if (ok) {
+                        if (ci < p.C0) {
+                            if (p.up0)
+                                src = p.src0 + ((size_t)(b * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.C0 + ci;
+                            else
+                                src = p.src0 + ((size_t)(b * p.H + iy) * p.W + ix) * p.C0 + ci;
+                        } else {
+                            src = p.src1 + ((size_t)(b * p.H + iy) * p.W + ix) * p.C1 + (ci - p.C0);
+                        }
+                    }
+                    mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                    const uint32_t row = stage_a_hi(s) + (uint32_t)r * 128u;
+                    const uint32_t nbytes = ok ? 16u : 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cp_async_16(row + (uint32_t)((j ^ (r & 7)) << 4), src + j * 4, nbytes);
+                    cp_async_mbar_arrive_noinc(smem_u32(&bars->full_a[s]));
+                    if (++s == p.stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 6 && warp < 10) {
+        // ================= converter: fp32 -> (hi, lo) tf32 planes =================
+        if (use_conv) {
+            const int ct = threadIdx.x - 6 * 32;  // 0..127
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(smem_u32(GATHER ? &bars->full_a[s] : &bars->full_b[s]), ph);
+                    if (p.three_x) {
+                        float4 *hi = reinterpret_cast<float4 *>(smem_gen + (size_t)s * stage_bytes);
+                        float4 *lo = reinterpret_cast<float4 *>(smem_gen + (size_t)s * stage_bytes + A_TILE_BYTES);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int idx = ct + i * 128;  // element-wise: the swizzled position is irrelevant
+                            const float4 v = hi[idx];
+                            float4 h, l;
+                            h.x = to_tf32_rna(v.x);
+                            h.y = to_tf32_rna(v.y);
+                            h.z = to_tf32_rna(v.z);
+                            h.w = to_tf32_rna(v.w);
+                            l.x = to_tf32_rna(v.x - h.x);
+                            l.y = to_tf32_rna(v.y - h.y);
+                            l.z = to_tf32_rna(v.z - h.z);
+                            l.w = to_tf32_rna(v.w - h.w);
+                            hi[idx] = h;
+                            lo[idx] = l;
+                        }
+                    }
+                    fence_proxy_async();  // generic-proxy writes (st.shared / cp.async) -> visible to the MMA (async proxy)
+                    mbar_arrive(smem_u32(&bars->conv[s]));
+                    if (++s == p.stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row_in_tile = q * 32 + lane;
+        const bool n_vec = (p.N & 3) == 0;
+        uint32_t acc_it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
+            const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+            const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+            mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
+            tc_fence_after();
+            const int m = mt * BM + row_in_tile;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)p.BN;
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t)c0, r);
+                tmem_ld_wait();
+                const int n = nt * p.BN + c0;
+                if (m < p.M && n < p.N) {
+                    float *out = p.dst + (size_t)m * p.N + n;
+                    const float *res = p.residual ? p.residual + (size_t)m * p.N + n : nullptr;
+                    if (n_vec && n + 15 < p.N) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + n + j));
+                            const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + n + j));
+                            float4 v;
+                            v.x = apply_act(fmaf(__uint_as_float(r[j]), sc.x, sh.x), p.act, p.alpha);
+                            v.y = apply_act(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y), p.act, p.alpha);
+                            v.z = apply_act(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z), p.act, p.alpha);
+                            v.w = apply_act(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w), p.act, p.alpha);
+                            if (res) {
+                                const float4 rr = __ldg(reinterpret_cast<const float4 *>(res + j));
+                                v.x += rr.x;
+                                v.y += rr.y;
+                                v.z += rr.z;
+                                v.w += rr.w;
+                            }
+                            *reinterpret_cast<float4 *>(out + j) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (n + j < p.N) {
+                                float v = apply_act(fmaf(__uint_as_float(r[j]), __ldg(p.scale + n + j), __ldg(p.shift + n + j)),
+                                                    p.act, p.alpha);
+                                if (res) v += __ldg(res + j);
+                                out[j] = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->tmem_empty[a]));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows][cols] tensor, box = [box_rows][32 cols], 128B swizzle, OOB -> 0.
+bool make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+float tf32_rna_host(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u = (u + 0x1000u) & 0xffffe000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+
+int g_num_sms = 0;
+size_t g_max_smem = 0;
+
+// Tile width: UMMA_N is a multiple of 16 and <= 256 (two accumulator stages must fit the 512 TMEM columns).
+// Big-M layers take the whole N in one tile (A streams from HBM exactly once); small-M layers (7x10 / 14x20
+// grids) split N so that the tile count approaches the SM count.
+int pick_bn(int M, int N) {
+    const int n16 = (N + 15) / 16 * 16;
+    const int m_tiles = (M + BM - 1) / BM;
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;
+    if (n16 <= 256 && (m_tiles * 4 >= sms * 3 || n16 <= 64)) return n16;
+    for (int bn : {256, 192, 128, 96, 64}) {
+        if (bn > n16) continue;
+        if (m_tiles * ((n16 + bn - 1) / bn) * 4 >= sms * 3) return bn;
+    }
+    return n16 < 64 ? n16 : 64;
+}
+
+int tc_init() {
+    if (g_num_sms != 0) return K2Y_OK;
+    int dev = 0;
+    K2Y_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    K2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)prop.sharedMemPerBlockOptin));
+    K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)prop.sharedMemPerBlockOptin));
+    g_max_smem = prop.sharedMemPerBlockOptin;
+    g_num_sms = prop.multiProcessorCount;
+    return K2Y_OK;
+}
+
+}  // namespace
+
+int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N) {
+    tc_free(w);
+    int rc = tc_init();
+    if (rc != K2Y_OK) return rc;
+    w.K = K;
+    w.N = N;
+    w.Kpad = (K + BK - 1) / BK * BK;
+    w.Npad = (N + 15) / 16 * 16;  // tiles wider than the remainder are zero-filled by TMA
+    std::vector<float> hi((size_t)w.Npad * w.Kpad, 0.f), lo((size_t)w.Npad * w.Kpad, 0.f);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) {
+            const float v = kernel_kn[(size_t)k * N + n];
+            const float h = tf32_rna_host(v);
+            hi[(size_t)n * w.Kpad + k] = h;
+            lo[(size_t)n * w.Kpad + k] = tf32_rna_host(v - h);
+        }
+    K2Y_CUDA_CHECK(cudaMalloc(&w.d_hi, hi.size() * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMalloc(&w.d_lo, lo.size() * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMemcpy(w.d_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+    K2Y_CUDA_CHECK(cudaMemcpy(w.d_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return K2Y_OK;
+}
+
+void tc_free(TcWeights &w) {
+    cudaFree(w.d_hi);
+    cudaFree(w.d_lo);
+    w = TcWeights();
+}
+
+static bool is_plain_1x1(const ConvArgs &a) {
+    return a.kh == 1 && a.kw == 1 && a.stride == 1 && a.src1 == nullptr && !a.up0 && a.pad_t == 0 && a.pad_l == 0;
+}
+
+bool tc_supported(const ConvArgs &a, const TcWeights &w) {
+    if (!w.d_hi || !get_encode()) return false;
+    const int Cin = a.C0 + a.C1;
+    if (is_plain_1x1(a)) return (Cin % 4) == 0 && (((uintptr_t)a.src0) & 15) == 0;  // TMA: 16-byte row pitch
+    // gather path: every k-block is one 128-byte channel run of one tap of one source
+    return (Cin % BK) == 0 && (a.C0 % BK) == 0 && (((uintptr_t)a.src0) & 15) == 0 &&
+           (a.src1 == nullptr || (((uintptr_t)a.src1) & 15) == 0);
+}
+
+cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st) {
+    if (g_num_sms == 0) return cudaErrorNotReady;
+    TcParams p;
+    p.src0 = a.src0;
+    p.src1 = a.src1;
+    p.H = a.H;
+    p.W = a.W;
+    p.C0 = a.C0;
+    p.C1 = a.C1;
+    p.up0 = a.up0;
+    p.OH = a.OH;
+    p.OW = a.OW;
+    p.kh = a.kh;
+    p.kw = a.kw;
+    p.stride = a.stride;
+    p.pad_t = a.pad_t;
+    p.pad_l = a.pad_l;
+    p.dst = a.dst;
+    p.residual = a.residual;
+    p.scale = a.scale;
+    p.shift = a.shift;
+    p.act = a.act;
+    p.alpha = a.alpha;
+    p.M = a.B * a.OH * a.OW;
+    p.N = a.N;
+    p.K = w.K;
+    p.BN = pick_bn(p.M, a.N);
+    p.n_tiles = (w.Npad + p.BN - 1) / p.BN;
+    p.m_tiles = (p.M + BM - 1) / BM;
+    p.nkb = w.Kpad / BK;
+    p.three_x = (math_mode == K2Y_MATH_TC_3XTF32) ? 1 : 0;
+    uint32_t cols = 32;
+    while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = (size_t)A_TILE_BYTES * (p.three_x ? 2 : 1) + (size_t)p.BN * 128 * (p.three_x ? 2 : 1);
+    const size_t fixed = 1024 + sizeof(Barriers) + 64;
+    int stages = (int)((g_max_smem - fixed) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return cudaErrorInvalidConfiguration;
+    p.stages = stages;
+    const size_t smem = fixed + (size_t)stages * stage_bytes;
+
+    const bool gather = !is_plain_1x1(a);
+    CUtensorMap map_a, map_bhi, map_blo;
+    memset(&map_a, 0, sizeof(map_a));
+    if (!gather && !make_map_2d(&map_a, a.src0, (uint64_t)p.M, (uint64_t)(a.C0 + a.C1), BM)) return cudaErrorInvalidValue;
+    if (!make_map_2d(&map_bhi, w.d_hi, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
+    if (!make_map_2d(&map_blo, w.d_lo, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
+
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    if (gather)
+        conv_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+    else
+        conv_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+    return cudaGetLastError();
+}
+
 }  // namespace k2y

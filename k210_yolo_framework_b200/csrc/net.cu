@@ -895,3 +895,80 @@ extern "C" int k2y_net_launch_info(const k2y_net *net, int i, char *name, int na
     if (bytes_per_image) *bytes_per_image = 4.0 * (in_elems + out_elems);  // algorithmic: activations read once + written once
     return K2Y_OK;
 }
+
+// Single-layer hook for kernel parity tests: one dense conv on device tensors, weights given in the Keras layout.
+extern "C" int k2y_conv2d(const float *src0_dev, const float *src1_dev, const float *residual_dev, float *dst_dev,
+                          const float *kernel_host, const float *scale_host, const float *shift_host, int batch, int h, int w,
+                          int c0, int c1, int up0, int cout, int ksize, int stride, int pad_mode, int act, float alpha,
+                          int math_mode, void *stream) {
+    if (!src0_dev || !dst_dev || !kernel_host || !scale_host || !shift_host || batch <= 0) {
+        set_error("k2y_conv2d: bad arguments");
+        return K2Y_ERR_INVALID;
+    }
+    ConvArgs a;
+    a.src0 = src0_dev;
+    a.src1 = c1 > 0 ? src1_dev : nullptr;
+    a.residual = residual_dev;
+    a.dst = dst_dev;
+    a.B = batch;
+    a.H = h;
+    a.W = w;
+    a.C0 = c0;
+    a.C1 = c1;
+    a.up0 = up0;
+    a.N = cout;
+    a.kh = a.kw = ksize;
+    a.stride = stride;
+    if (pad_mode == 0) {
+        a.pad_t = a.pad_l = ksize / 2;
+        a.OH = h;
+        a.OW = w;
+    } else if (pad_mode == 1) {
+        a.pad_t = a.pad_l = 1;
+        a.OH = (h + 2 - ksize) / stride + 1;
+        a.OW = (w + 2 - ksize) / stride + 1;
+    } else {
+        a.pad_t = a.pad_l = 1;
+        a.OH = (h + 1 - ksize) / stride + 1;
+        a.OW = (w + 1 - ksize) / stride + 1;
+    }
+    a.act = act;
+    a.alpha = alpha;
+    const int K = ksize * ksize * (c0 + c1);
+    float *d_w = nullptr, *d_sc = nullptr, *d_sh = nullptr;
+    K2Y_CUDA_CHECK(cudaMalloc(&d_w, (size_t)K * cout * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMalloc(&d_sc, cout * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMalloc(&d_sh, cout * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMemcpy(d_w, kernel_host, (size_t)K * cout * sizeof(float), cudaMemcpyHostToDevice));
+    K2Y_CUDA_CHECK(cudaMemcpy(d_sc, scale_host, cout * sizeof(float), cudaMemcpyHostToDevice));
+    K2Y_CUDA_CHECK(cudaMemcpy(d_sh, shift_host, cout * sizeof(float), cudaMemcpyHostToDevice));
+    a.w = d_w;
+    a.scale = d_sc;
+    a.shift = d_sh;
+    TcWeights tw;
+    int rc = K2Y_OK;
+    cudaError_t e = cudaSuccess;
+    if (math_mode == K2Y_MATH_FP32_SIMT) {
+        e = launch_conv_simt(a, (cudaStream_t)stream);
+    } else {
+        rc = tc_pack(tw, kernel_host, K, cout);
+        if (rc == K2Y_OK) {
+            if (!tc_supported(a, tw)) {
+                set_error("k2y_conv2d: shape not supported by the tensor-core path");
+                rc = K2Y_ERR_INVALID;
+            } else {
+                e = launch_conv_tc(a, tw, math_mode, (cudaStream_t)stream);
+            }
+        }
+    }
+    if (rc == K2Y_OK && e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (rc == K2Y_OK && e != cudaSuccess) {
+        set_error("k2y_conv2d: %s", cudaGetErrorString(e));
+        rc = K2Y_ERR_CUDA;
+    }
+    tc_free(tw);
+    cudaFree(d_w);
+    cudaFree(d_sc);
+    cudaFree(d_sh);
+    return rc;
+}
