@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--math", choices=["fp32_simt", "tc_3xtf32", "tc_tf32"], default=os.environ.get("K2Y_BENCH_MATH", "fp32_simt"))
+    ap.add_argument("--math", choices=["fp32_simt", "tc_3xtf32", "tc_tf32"], default=os.environ.get("K2Y_BENCH_MATH", "tc_3xtf32"))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -200,44 +200,125 @@ __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const ConvArgs a) 
     }
 }
 
-// Depthwise 3x3: one thread per (output pixel, 4 channels).
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs a) {
+// Depthwise 3x3, NHWC fp32: one thread = 4 channels x TX consecutive output pixels of one output row.
+// The 9 per-channel taps live in registers and every input column is loaded once per row (TX + 2 columns for
+// stride 1, 2*TX + 1 for stride 2 instead of 9 per output), which takes the kernel off the instruction-issue
+// limit and onto the HBM roofline.  grid = (ceil(XT*C4 / 128), B*OH).
+template <int STRIDE, int TX>
+__global__ void __launch_bounds__(128) dwconv3x3_kernel(const DwArgs a) {
+    constexpr int NCOL = (TX - 1) * STRIDE + 3;
     const int c4n = a.C >> 2;
-    const size_t total = (size_t)a.B * a.OH * a.OW * c4n;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % c4n) * 4;
-    size_t p = idx / c4n;
-    const int ox = (int)(p % a.OW);
-    p /= a.OW;
-    const int oy = (int)(p % a.OH);
-    const int b = (int)(p / a.OH);
-    const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int xt_n = (a.OW + TX - 1) / TX;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= xt_n * c4n) return;
+    const int c = (idx % c4n) * 4;
+    const int ox0 = (idx / c4n) * TX;
+    const int row = blockIdx.y;  // b * OH + oy
+    const int oy = row % a.OH, b = row / a.OH;
+    const int iy0 = oy * STRIDE - a.pad_t, ix0 = ox0 * STRIDE - a.pad_l;
+
+    float4 w[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float4 *>(a.w + t * a.C + c));
+    float4 acc[TX];
+#pragma unroll
+    for (int i = 0; i < TX; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int iy = iy0 + ky;
         if (iy < 0 || iy >= a.H) continue;
+        const float *rowp = a.src + ((size_t)(b * a.H + iy) * a.W) * a.C + c;
+        float4 col[NCOL];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int ix = ix0 + kx;
-            if (ix < 0 || ix >= a.W) continue;
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(a.src + ((size_t)(b * a.H + iy) * a.W + ix) * a.C + c));
-            const float4 w = __ldg(reinterpret_cast<const float4 *>(a.w + (ky * 3 + kx) * a.C + c));
-            acc.x = fmaf(v.x, w.x, acc.x);
-            acc.y = fmaf(v.y, w.y, acc.y);
-            acc.z = fmaf(v.z, w.z, acc.z);
-            acc.w = fmaf(v.w, w.w, acc.w);
+        for (int j = 0; j < NCOL; ++j) {
+            const int ix = ix0 + j;
+            col[j] = (ix >= 0 && ix < a.W) ? __ldg(reinterpret_cast<const float4 *>(rowp + (size_t)ix * a.C))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 v = col[i * STRIDE + kx];
+                const float4 ww = w[ky * 3 + kx];
+                acc[i].x = fmaf(v.x, ww.x, acc[i].x);
+                acc[i].y = fmaf(v.y, ww.y, acc[i].y);
+                acc[i].z = fmaf(v.z, ww.z, acc[i].z);
+                acc[i].w = fmaf(v.w, ww.w, acc[i].w);
+            }
         }
     }
     const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale + c));
     const float4 sh = __ldg(reinterpret_cast<const float4 *>(a.shift + c));
-    float4 o;
-    o.x = apply_act(fmaf(acc.x, sc.x, sh.x), a.act, a.alpha);
-    o.y = apply_act(fmaf(acc.y, sc.y, sh.y), a.act, a.alpha);
-    o.z = apply_act(fmaf(acc.z, sc.z, sh.z), a.act, a.alpha);
-    o.w = apply_act(fmaf(acc.w, sc.w, sh.w), a.act, a.alpha);
-    *reinterpret_cast<float4 *>(a.dst + ((size_t)(b * a.OH + oy) * a.OW + ox) * a.C + c) = o;
+    float *outp = a.dst + ((size_t)row * a.OW) * a.C + c;
+#pragma unroll
+    for (int i = 0; i < TX; ++i) {
+        const int ox = ox0 + i;
+        if (ox >= a.OW) break;
+        float4 o;
+        o.x = apply_act(fmaf(acc[i].x, sc.x, sh.x), a.act, a.alpha);
+        o.y = apply_act(fmaf(acc[i].y, sc.y, sh.y), a.act, a.alpha);
+        o.z = apply_act(fmaf(acc[i].z, sc.z, sh.z), a.act, a.alpha);
+        o.w = apply_act(fmaf(acc[i].w, sc.w, sh.w), a.act, a.alpha);
+        *reinterpret_cast<float4 *>(outp + (size_t)ox * a.C) = o;
+    }
+}
+
+// First convolution of every network: 3x3, Cin = 3, Cout in {16, 24, 32}.  One thread = one output pixel, all
+// output channels; the 27 x COUT weights sit in shared memory and are read as warp-wide broadcasts.
+template <int COUT>
+__global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a) {
+    __shared__ __align__(16) float ws[27 * COUT];
+    __shared__ __align__(16) float sc[COUT], sh[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) ws[i] = a.w[i];
+    if (threadIdx.x < COUT) {
+        sc[threadIdx.x] = a.scale[threadIdx.x];
+        sh[threadIdx.x] = a.shift[threadIdx.x];
+    }
+    __syncthreads();
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ox >= a.OW) return;
+    const int row = blockIdx.y;
+    const int oy = row % a.OH, b = row / a.OH;
+    const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
+    float in[27];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = iy0 + ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ix0 + kx;
+            const bool ok = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+            const float *p = a.src0 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) in[(ky * 3 + kx) * 3 + ci] = ok ? __ldg(p + ci) : 0.f;
+        }
+    }
+    float acc[COUT];
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+#pragma unroll
+        for (int n = 0; n < COUT; n += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(&ws[k * COUT + n]);
+            acc[n] = fmaf(in[k], wv.x, acc[n]);
+            acc[n + 1] = fmaf(in[k], wv.y, acc[n + 1]);
+            acc[n + 2] = fmaf(in[k], wv.z, acc[n + 2]);
+            acc[n + 3] = fmaf(in[k], wv.w, acc[n + 3]);
+        }
+    }
+    float *outp = a.dst + ((size_t)row * a.OW + ox) * COUT;
+#pragma unroll
+    for (int n = 0; n < COUT; n += 4) {
+        float4 o;
+        o.x = apply_act(fmaf(acc[n], sc[n], sh[n]), a.act, a.alpha);
+        o.y = apply_act(fmaf(acc[n + 1], sc[n + 1], sh[n + 1]), a.act, a.alpha);
+        o.z = apply_act(fmaf(acc[n + 2], sc[n + 2], sh[n + 2]), a.act, a.alpha);
+        o.w = apply_act(fmaf(acc[n + 3], sc[n + 3], sh[n + 3]), a.act, a.alpha);
+        *reinterpret_cast<float4 *>(outp + n) = o;
+    }
 }
 
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const PoolArgs a) {
@@ -275,6 +356,13 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const PoolArgs a) {
 
 cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
     const int M = a.B * a.OH * a.OW;
+    if (a.kh == 3 && a.kw == 3 && a.C0 == 3 && a.C1 == 0 && !a.up0 && !a.residual && (a.N == 16 || a.N == 24 || a.N == 32)) {
+        dim3 grid((a.OW + 127) / 128, a.B * a.OH);
+        if (a.N == 16) first_conv3x3_kernel<16><<<grid, 128, 0, st>>>(a);
+        else if (a.N == 24) first_conv3x3_kernel<24><<<grid, 128, 0, st>>>(a);
+        else first_conv3x3_kernel<32><<<grid, 128, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     const bool vec = (a.C0 % 4 == 0) && (a.C1 % 4 == 0);
     const int gy = (a.N + BN_T - 1) / BN_T;
     // Small-M layers (7x10 / 14x20 grids) use 64-row tiles so that the grid still covers 148 SMs.
@@ -296,8 +384,13 @@ cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
 }
 
 cudaError_t launch_dwconv(const DwArgs &a, cudaStream_t st) {
-    const size_t total = (size_t)a.B * a.OH * a.OW * (a.C / 4);
-    dwconv3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    constexpr int TX = 4;
+    const int per_row = ((a.OW + TX - 1) / TX) * (a.C / 4);
+    dim3 grid((per_row + 127) / 128, a.B * a.OH);
+    if (a.stride == 1)
+        dwconv3x3_kernel<1, TX><<<grid, 128, 0, st>>>(a);
+    else
+        dwconv3x3_kernel<2, TX><<<grid, 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -18,6 +18,8 @@ namespace k2y {
 namespace {
 
 constexpr int DET_THREADS = 1024;
+constexpr int DET_WARPS = 4;          // classes per CTA in the KERAS kernel
+constexpr int DET_SMEM_KEYS = 4096;   // per-warp key capacity in shared memory (32 KB)
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
@@ -109,9 +111,8 @@ struct KerasParams {
     const float *image_hw;
     k2y_det *dets;
     int *counts;
-    float4 *boxes;              // [B][nbox]
-    float *scores;              // [B][C][nbox]
-    unsigned long long *keys;   // [B][C][P]
+    unsigned long long *keys_global;  // [B][C][P] — only used when P does not fit shared memory
+    int keys_in_smem;
 };
 
 // Collects the candidates of one class (score passes `pred`) in index order, sorts them.
@@ -143,73 +144,116 @@ __device__ __forceinline__ int gather_sorted(const float *sc, int nbox, float th
     return n;
 }
 
-__global__ void __launch_bounds__(DET_THREADS) detect_keras_kernel(const KerasParams p) {
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int E = 5 + p.C;
-    float4 *boxes = p.boxes + (size_t)b * p.nbox;
-    float *scores = p.scores + (size_t)b * p.C * p.nbox;
+struct BoxXform {  // correct_box constants of one image (keras_inference.py:53-58)
+    float img_h, img_w, off_y, off_x, sc_y, sc_x;
+};
 
-    // correct_box constants for this image (keras_inference.py:53-58), float32, same op order.
-    const float img_h = p.image_hw[2 * b], img_w = p.image_hw[2 * b + 1];
-    const float r = fminf(__fdiv_rn(p.in_h, img_h), __fdiv_rn(p.in_w, img_w));
-    const float new_h = rintf(__fmul_rn(img_h, r)), new_w = rintf(__fmul_rn(img_w, r));
-    const float off_y = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_h, new_h), 2.0f), p.in_h);
-    const float off_x = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_w, new_w), 2.0f), p.in_w);
-    const float sc_y = __fdiv_rn(p.in_h, new_h), sc_x = __fdiv_rn(p.in_w, new_w);
+__device__ __forceinline__ const float *box_entry(const KerasParams &p, int b, int box, int &l, int &a, int &col, int &row) {
+    l = 0;
+    if (p.n_layers > 1 && box >= p.loff[1]) l = 1;
+    if (p.n_layers > 2 && box >= p.loff[2]) l = 2;
+    const int local = box - p.loff[l];
+    a = local % p.A;
+    const int cell = local / p.A;
+    const int W = p.lw[l];
+    col = cell % W;
+    row = cell / W;
+    return p.heads[l] + ((size_t)((size_t)b * p.lh[l] * W + cell) * p.A + a) * (5 + p.C);
+}
 
-    // ---- phase 1: decode ----
-    for (int box = tid; box < p.nbox; box += DET_THREADS) {
-        int l = 0;
-        if (p.n_layers > 1 && box >= p.loff[1]) l = 1;
-        if (p.n_layers > 2 && box >= p.loff[2]) l = 2;
-        const int local = box - p.loff[l];
-        const int a = local % p.A;
-        const int cell = local / p.A;
-        const int W = p.lw[l], H = p.lh[l];
-        const int col = cell % W, row = cell / W;
-        const float *e = p.heads[l] + ((size_t)((size_t)b * H * W + cell) * p.A + a) * E;
-        const float tx = __ldg(e), ty = __ldg(e + 1), tw = __ldg(e + 2), th = __ldg(e + 3), tc = __ldg(e + 4);
-        // tf_xywh_to_all (tools/utils.py:545-546)
-        const float x = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)W);
-        const float y = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)H);
-        const float w = __fmul_rn(expf(tw), p.anchors[(l * p.A + a) * 2]);
-        const float h = __fmul_rn(expf(th), p.anchors[(l * p.A + a) * 2 + 1]);
-        // correct_box (keras_inference.py:59-71)
-        const float cy = __fmul_rn(__fsub_rn(y, off_y), sc_y), cx = __fmul_rn(__fsub_rn(x, off_x), sc_x);
-        const float hh = __fmul_rn(h, sc_y), ww = __fmul_rn(w, sc_x);
-        const float hh2 = __fdiv_rn(hh, 2.0f), ww2 = __fdiv_rn(ww, 2.0f);
-        float4 bx;
-        bx.x = __fmul_rn(__fsub_rn(cy, hh2), img_h);
-        bx.y = __fmul_rn(__fsub_rn(cx, ww2), img_w);
-        bx.z = __fmul_rn(__fadd_rn(cy, hh2), img_h);
-        bx.w = __fmul_rn(__fadd_rn(cx, ww2), img_w);
-        boxes[box] = bx;
-        const float sconf = sigmoidf_ref(tc);
-        for (int c = 0; c < p.C; ++c) scores[(size_t)c * p.nbox + box] = __fmul_rn(sigmoidf_ref(__ldg(e + 5 + c)), sconf);
+// tf_xywh_to_all (tools/utils.py:545-546) + correct_box (keras_inference.py:59-71) for one box.
+__device__ __forceinline__ float4 decode_box(const KerasParams &p, const BoxXform &x, int b, int box) {
+    int l, a, col, row;
+    const float *e = box_entry(p, b, box, l, a, col, row);
+    const float tx = __ldg(e), ty = __ldg(e + 1), tw = __ldg(e + 2), th = __ldg(e + 3);
+    const float bx = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)p.lw[l]);
+    const float by = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)p.lh[l]);
+    const float bw = __fmul_rn(expf(tw), p.anchors[(l * p.A + a) * 2]);
+    const float bh = __fmul_rn(expf(th), p.anchors[(l * p.A + a) * 2 + 1]);
+    const float cy = __fmul_rn(__fsub_rn(by, x.off_y), x.sc_y), cx = __fmul_rn(__fsub_rn(bx, x.off_x), x.sc_x);
+    const float hh2 = __fdiv_rn(__fmul_rn(bh, x.sc_y), 2.0f), ww2 = __fdiv_rn(__fmul_rn(bw, x.sc_x), 2.0f);
+    float4 r;
+    r.x = __fmul_rn(__fsub_rn(cy, hh2), x.img_h);
+    r.y = __fmul_rn(__fsub_rn(cx, ww2), x.img_w);
+    r.z = __fmul_rn(__fadd_rn(cy, hh2), x.img_h);
+    r.w = __fmul_rn(__fadd_rn(cx, ww2), x.img_w);
+    return r;
+}
+
+// grid = (ceil(C / warps), B): one warp owns one (image, class).  It scans the head tensors for its class
+// (score = sigmoid(cls) * sigmoid(conf)), compacts the candidates in index order into sort keys, sorts them, decodes
+// the candidate boxes 32 at a time (one per lane) and runs the greedy suppression with shuffles.
+__global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const KerasParams p) {
+    extern __shared__ __align__(16) unsigned long long smem_keys[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * DET_WARPS + warp;
+    if (c >= p.C) return;
+    unsigned long long *keys = p.keys_in_smem ? smem_keys + (size_t)warp * p.P : p.keys_global + ((size_t)b * p.C + c) * p.P;
+
+    BoxXform x;
+    x.img_h = p.image_hw[2 * b];
+    x.img_w = p.image_hw[2 * b + 1];
+    const float r = fminf(__fdiv_rn(p.in_h, x.img_h), __fdiv_rn(p.in_w, x.img_w));
+    const float new_h = rintf(__fmul_rn(x.img_h, r)), new_w = rintf(__fmul_rn(x.img_w, r));
+    x.off_y = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_h, new_h), 2.0f), p.in_h);
+    x.off_x = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_w, new_w), 2.0f), p.in_w);
+    x.sc_y = __fdiv_rn(p.in_h, new_h);
+    x.sc_x = __fdiv_rn(p.in_w, new_w);
+
+    // ---- scan: candidates of class c in index order ----
+    int n = 0;
+    for (int base = 0; base < p.nbox; base += 32) {
+        const int box = base + lane;
+        bool pass = false;
+        float s = 0.f;
+        if (box < p.nbox) {
+            int l, a, col, row;
+            const float *e = box_entry(p, b, box, l, a, col, row);
+            s = __fmul_rn(sigmoidf_ref(__ldg(e + 5 + c)), sigmoidf_ref(__ldg(e + 4)));
+            pass = s >= p.obj;
+        }
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (pass) keys[n + __popc(m & ((1u << lane) - 1u))] = pack_key(s, box);
+        n += __popc(m);
     }
-    __syncthreads();
+    __syncwarp();
+    unsigned long long rkey = 0ull;
+    if (n <= 32) {
+        if (lane < n) rkey = keys[lane];
+        rkey = warp_sort_desc(rkey, lane);
+    } else {
+        int P = 64;
+        while (P < n) P <<= 1;
+        for (int i = n + lane; i < P; i += 32) keys[i] = 0ull;
+        __syncwarp();
+        warp_sort_desc_mem(keys, P, lane);
+    }
 
-    // ---- phase 2: per-class NMS, one warp per class ----
-    const int warp = tid >> 5, lane = tid & 31, nwarps = DET_THREADS >> 5;
-    for (int c = warp; c < p.C; c += nwarps) {
-        unsigned long long *keys = p.keys + ((size_t)b * p.C + c) * p.P;
-        unsigned long long rkey;
-        const int n = gather_sorted<true>(scores + (size_t)c * p.nbox, p.nbox, p.obj, keys, lane, rkey);
-        k2y_det *out = p.dets + ((size_t)b * p.C + c) * p.maxk;
-        float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f);
-        int nsel = 0;
-        for (int i = 0; i < n && nsel < p.maxk; ++i) {
-            const unsigned long long key = (n <= 32) ? __shfl_sync(FULL, rkey, i) : keys[i];
-            const int idx = key_index(key);
-            const float4 cb = boxes[idx];
-            bool sup = (lane < nsel) && (iou_yxyx(cb, mybox) > p.iou);  // first 32 kept boxes live in registers
+    // ---- greedy NMS over the sorted candidates, 32 at a time ----
+    k2y_det *out = p.dets + ((size_t)b * p.C + c) * p.maxk;
+    float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f);  // lane s holds kept box s (first 32)
+    int nsel = 0;
+    for (int base = 0; base < n && nsel < p.maxk; base += 32) {
+        const int i = base + lane;
+        const unsigned long long mykey = (n <= 32) ? rkey : (i < n ? keys[i] : 0ull);
+        float4 cand = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) cand = decode_box(p, x, b, key_index(mykey));
+        const int cnt = min(32, n - base);
+        for (int j = 0; j < cnt && nsel < p.maxk; ++j) {
+            float4 cb;
+            cb.x = __shfl_sync(FULL, cand.x, j);
+            cb.y = __shfl_sync(FULL, cand.y, j);
+            cb.z = __shfl_sync(FULL, cand.z, j);
+            cb.w = __shfl_sync(FULL, cand.w, j);
+            const unsigned long long key = __shfl_sync(FULL, mykey, j);
+            bool sup = (lane < nsel) && (iou_yxyx(cb, mybox) > p.iou);
             bool any = __ballot_sync(FULL, sup) != 0u;
-            for (int base = 32; !any && base < nsel; base += 32) {  // only when max_per_class > 32
-                const int j = base + lane;
+            for (int sb = 32; !any && sb < nsel; sb += 32) {  // only when max_per_class > 32
+                const int k = sb + lane;
                 sup = false;
-                if (j < nsel) {
-                    const k2y_det d = out[j];
+                if (k < nsel) {
+                    const k2y_det d = out[k];
                     sup = iou_yxyx(cb, make_float4(d.ymin, d.xmin, d.ymax, d.xmax)) > p.iou;
                 }
                 any = __ballot_sync(FULL, sup) != 0u;
@@ -223,15 +267,15 @@ __global__ void __launch_bounds__(DET_THREADS) detect_keras_kernel(const KerasPa
                     d.ymax = cb.z;
                     d.xmax = cb.w;
                     d.score = key_score(key);
-                    d.index = idx;
+                    d.index = key_index(key);
                     out[nsel] = d;
                 }
                 ++nsel;
                 __syncwarp();
             }
         }
-        if (lane == 0) p.counts[b * p.C + c] = nsel;
     }
+    if (lane == 0) p.counts[b * p.C + c] = nsel;
 }
 
 struct RegionParams {
@@ -356,8 +400,8 @@ extern "C" int k2y_detect_workspace_bytes(const k2y_detect_cfg *cfg, int batch, 
     size_t nbox = 0;
     for (int l = 0; l < cfg->n_layers; ++l) nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
     const size_t P = next_pow2((int)nbox);
-    *bytes = align256((size_t)batch * nbox * sizeof(float4)) + align256((size_t)batch * cfg->class_num * nbox * sizeof(float)) +
-             align256((size_t)batch * cfg->class_num * P * sizeof(unsigned long long));
+    // sort keys live in shared memory up to DET_SMEM_KEYS boxes per image; larger grids spill them to this workspace
+    *bytes = 256 + (P > (size_t)DET_SMEM_KEYS ? align256((size_t)batch * cfg->class_num * P * sizeof(unsigned long long)) : 0);
     return K2Y_OK;
 }
 
@@ -400,13 +444,17 @@ extern "C" int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *h
     p.image_hw = image_hw_dev;
     p.dets = dets_dev;
     p.counts = counts_dev;
-    char *ws = (char *)workspace;
-    p.boxes = (float4 *)ws;
-    ws += align256((size_t)batch * p.nbox * sizeof(float4));
-    p.scores = (float *)ws;
-    ws += align256((size_t)batch * p.C * p.nbox * sizeof(float));
-    p.keys = (unsigned long long *)ws;
-    detect_keras_kernel<<<batch, DET_THREADS, 0, (cudaStream_t)stream>>>(p);
+    p.keys_in_smem = p.P <= DET_SMEM_KEYS ? 1 : 0;
+    p.keys_global = (unsigned long long *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const size_t smem = p.keys_in_smem ? (size_t)DET_WARPS * p.P * sizeof(unsigned long long) : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_keras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(DET_WARPS * DET_SMEM_KEYS * sizeof(unsigned long long))));
+        attr_set = true;
+    }
+    dim3 grid((p.C + DET_WARPS - 1) / DET_WARPS, batch);
+    detect_keras_kernel<<<grid, DET_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
     K2Y_CUDA_CHECK(cudaGetLastError());
     return K2Y_OK;
 }

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -115,12 +116,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Branch-free activation: y = min(max(v,0) + slope*min(v,0), clamp)
+//   none: slope 1, clamp inf | leaky: slope alpha | relu: slope 0 | relu6: slope 0, clamp 6
+__device__ __forceinline__ float act_bf(float v, float slope, float clamp) {
+    return fminf(fmaxf(v, 0.f) + slope * fminf(v, 0.f), clamp);
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Round-to-nearest (ties away) to tf32 with two full-rate integer ops; cvt.rna.tf32.f32 issues at quarter rate and
+// made the converter warps the per-k-block bottleneck (64 conversions per thread).
 __device__ __forceinline__ float to_tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -155,7 +179,21 @@ struct TcParams {
     int BN, n_tiles, m_tiles, nkb, stages;
     int three_x;                    // 1 = 3xTF32, 0 = single pass
     uint32_t tmem_cols;
+    float act_slope, act_clamp;     // branch-free activation parameters
+    int tma_store;                  // 1: epilogue writes through a TMA store (N % 4 == 0, no residual)
+    int dbg;                        // bring-up switches (K2Y_TC_DBG): 1 skip stores, 2 skip tmem loads, 4 skip convert math
+    long long *trace;               // optional [gridDim.x][16] globaltimer stamps (K2Y_TC_TRACE=1 via k2y_conv2d)
 };
+
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define K2Y_TRACE(slot)                                                                  \
+    do {                                                                                 \
+        if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtime();                \
+    } while (0)
 
 struct __align__(8) Barriers {
     uint64_t full_b[MAX_STAGES], full_a[MAX_STAGES], conv[MAX_STAGES], empty[MAX_STAGES];
@@ -166,7 +204,8 @@ struct __align__(8) Barriers {
 template <bool GATHER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-               const __grid_constant__ CUtensorMap map_blo, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
+               const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages] x { A_hi(raw) 16K | A_lo 16K (3x) | B_hi BN*128 | B_lo BN*128 (3x) }, then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -179,6 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool use_conv = p.three_x || GATHER;
 
     if (threadIdx.x == 0) {
+        K2Y_TRACE(0);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bars->full_b[s]), 1);
             mbar_init(smem_u32(&bars->full_a[s]), 128);
@@ -193,12 +233,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (!GATHER) prefetch_tmap(&map_a);
         prefetch_tmap(&map_bhi);
         if (p.three_x) prefetch_tmap(&map_blo);
+        if (p.tma_store) prefetch_tmap(&map_out);
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_slot), p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_slot;
+    if (threadIdx.x == 0) K2Y_TRACE(1);
 
     const int num_tiles = p.m_tiles * p.n_tiles;
     auto stage_a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
@@ -221,6 +263,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (!GATHER) tma_load_2d(stage_a_hi(s), &map_a, fb, kb * BK, mt * BM);
                     tma_load_2d(stage_b_hi(s), &map_bhi, fb, kb * BK, nt * p.BN);
                     if (p.three_x) tma_load_2d(stage_b_lo(s), &map_blo, fb, kb * BK, nt * p.BN);
+                    if (t == (int)blockIdx.x && kb == 0) K2Y_TRACE(2);
+                    if (t == (int)blockIdx.x && kb == p.nkb - 1) K2Y_TRACE(3);
                     if (++s == p.stages) {
                         s = 0;
                         ph ^= 1u;
@@ -241,7 +285,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t d = tmem_base + a * (uint32_t)p.BN;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(smem_u32(&bars->full_b[s]), ph);
+                    if (t == (int)blockIdx.x && kb == 0) K2Y_TRACE(4);
                     if (use_conv) mbar_wait(smem_u32(&bars->conv[s]), ph);
+                    if (t == (int)blockIdx.x && kb == 0) K2Y_TRACE(5);
                     tc_fence_after();
                     const uint64_t a_hi = make_desc_sw128(stage_a_hi(s)), b_hi = make_desc_sw128(stage_b_hi(s));
                     const uint64_t a_lo = make_desc_sw128(stage_a_lo(s)), b_lo = make_desc_sw128(stage_b_lo(s));
@@ -264,7 +310,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
                 umma_commit(smem_u32(&bars->tmem_full[a]));
+                if (t == (int)blockIdx.x) K2Y_TRACE(6);
             }
+            K2Y_TRACE(7);
         }
     } else if (warp >= 2 && warp < 6) {
         // ================= A gather (implicit GEMM rows) =================
@@ -326,7 +374,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(smem_u32(GATHER ? &bars->full_a[s] : &bars->full_b[s]), ph);
-                    if (p.three_x) {
+                    if (p.three_x && !(p.dbg & 4)) {
                         float4 *hi = reinterpret_cast<float4 *>(smem_gen + (size_t)s * stage_bytes);
                         float4 *lo = reinterpret_cast<float4 *>(smem_gen + (size_t)s * stage_bytes + A_TILE_BYTES);
 #pragma unroll
@@ -357,67 +405,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ================= epilogue =================
+        // TMEM -> registers (lane = GEMM row) -> BN-fold/activation -> 128B-swizzled smem staging [32 rows][32 cols]
+        // per warp -> either one TMA store per 32-column chunk (full-line writes, no LSU work) or, for N % 4 != 0 /
+        // residual layers, row-contiguous st.global (a warp instruction covers 4 rows x 128 contiguous bytes).
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int row_in_tile = q * 32 + lane;
         const bool n_vec = (p.N & 3) == 0;
-        uint32_t acc_it = 0;
+        // two 4 KB staging buffers per warp, 1024-byte aligned (SWIZZLE_128B atom)
+        const uint32_t stg_base = ((smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)sizeof(Barriers) + 1023u) & ~1023u) +
+                                  (uint32_t)(warp - 10) * 8192u;
+        const int chunk = lane & 7, rsub = lane >> 3;
+        uint32_t acc_it = 0, stg_it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
             const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
             const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
             mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
+            if (t == (int)blockIdx.x && threadIdx.x == 10 * 32) K2Y_TRACE(8);
             tc_fence_after();
-            const int m = mt * BM + row_in_tile;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)p.BN;
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t)c0, r);
+            const int m_base = mt * BM + q * 32;
+            for (int c0 = 0; c0 < p.BN; c0 += 32, ++stg_it) {
+                const int ncols = (p.BN - c0) < 32 ? (p.BN - c0) : 32;  // 32 or 16
+                const int n0 = nt * p.BN + c0;
+                const uint32_t stg = stg_base + (stg_it & 1u) * 4096u;
+                uint32_t r[32];
+                tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                if (ncols == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+                else {
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) r[j] = 0u;
+                }
                 tmem_ld_wait();
-                const int n = nt * p.BN + c0;
-                if (m < p.M && n < p.N) {
-                    float *out = p.dst + (size_t)m * p.N + n;
-                    const float *res = p.residual ? p.residual + (size_t)m * p.N + n : nullptr;
-                    if (n_vec && n + 15 < p.N) {
+                if (p.tma_store) {
+                    // scale/shift are warp-uniform broadcasts (same address in every lane)
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + n + j));
-                            const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + n + j));
-                            float4 v;
-                            v.x = apply_act(fmaf(__uint_as_float(r[j]), sc.x, sh.x), p.act, p.alpha);
-                            v.y = apply_act(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y), p.act, p.alpha);
-                            v.z = apply_act(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z), p.act, p.alpha);
-                            v.w = apply_act(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w), p.act, p.alpha);
-                            if (res) {
-                                const float4 rr = __ldg(reinterpret_cast<const float4 *>(res + j));
-                                v.x += rr.x;
-                                v.y += rr.y;
-                                v.z += rr.z;
-                                v.w += rr.w;
-                            }
-                            *reinterpret_cast<float4 *>(out + j) = v;
+                    for (int j = 0; j < 32; j += 4) {
+                        if (n0 + j < p.N) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(p.scale + n0 + j));
+                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(p.shift + n0 + j));
+                            r[j] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j]), s4.x, h4.x), p.act_slope, p.act_clamp));
+                            r[j + 1] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j + 1]), s4.y, h4.y), p.act_slope, p.act_clamp));
+                            r[j + 2] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j + 2]), s4.z, h4.z), p.act_slope, p.act_clamp));
+                            r[j + 3] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j + 3]), s4.w, h4.w), p.act_slope, p.act_clamp));
                         }
-                    } else {
+                    }
+                    // the staging buffer used two chunks ago must have been read by its TMA store
+                    if (lane == 0) tma_store_wait_read1();
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[j * 4], r[j * 4 + 1],
+                                     r[j * 4 + 2], r[j * 4 + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && !(p.dbg & 1)) {
+                        tma_store_2d(&map_out, stg, n0, m_base);  // rows >= M and columns >= N are clipped by the TMA
+                        tma_store_commit();
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[j * 4], r[j * 4 + 1],
+                                     r[j * 4 + 2], r[j * 4 + 3]);
+                    __syncwarp();
+                    const int n = n0 + chunk * 4;
+                    const bool col_ok = (chunk * 4 < ncols) && (n < p.N);
+                    const bool full4 = n_vec && (n + 3 < p.N);
+                    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
                             if (n + j < p.N) {
-                                float v = apply_act(fmaf(__uint_as_float(r[j]), __ldg(p.scale + n + j), __ldg(p.shift + n + j)),
-                                                    p.act, p.alpha);
-                                if (res) v += __ldg(res + j);
-                                out[j] = v;
+                                sc[j] = __ldg(p.scale + n + j);
+                                sh[j] = __ldg(p.shift + n + j);
+                            }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + rsub;
+                        const int m = m_base + row;
+                        const float4 v = ld_shared_v4(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
+                        if (col_ok && m < p.M && !(p.dbg & 1)) {
+                            float o[4];
+                            o[0] = act_bf(fmaf(v.x, sc[0], sh[0]), p.act_slope, p.act_clamp);
+                            o[1] = act_bf(fmaf(v.y, sc[1], sh[1]), p.act_slope, p.act_clamp);
+                            o[2] = act_bf(fmaf(v.z, sc[2], sh[2]), p.act_slope, p.act_clamp);
+                            o[3] = act_bf(fmaf(v.w, sc[3], sh[3]), p.act_slope, p.act_clamp);
+                            float *out = p.dst + (size_t)m * p.N + n;
+                            if (full4) {
+                                if (p.residual) {
+                                    const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + (size_t)m * p.N + n));
+                                    o[0] += rr.x, o[1] += rr.y, o[2] += rr.z, o[3] += rr.w;
+                                }
+                                *reinterpret_cast<float4 *>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (n + j < p.N) out[j] = o[j] + (p.residual ? __ldg(p.residual + (size_t)m * p.N + n + j) : 0.f);
                             }
                         }
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->tmem_empty[a]));
+            if (t == (int)blockIdx.x && threadIdx.x == 10 * 32) K2Y_TRACE(9);
         }
+        if (p.tma_store && lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
+        if (threadIdx.x == 10 * 32) K2Y_TRACE(10);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) K2Y_TRACE(11);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
+        if (lane == 0) K2Y_TRACE(12);
     }
 }
 
@@ -441,17 +545,23 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 row-major [rows][cols] tensor, box = [box_rows][32 cols], 128B swizzle, OOB -> 0.
-bool make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+bool make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t pitch_elems = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint64_t strides[1] = {(pitch_elems ? pitch_elems : cols) * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+float __int_as_float_host(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
 }
 
 float tf32_rna_host(float x) {
@@ -470,16 +580,34 @@ size_t g_max_smem = 0;
 // Tile width: UMMA_N is a multiple of 16 and <= 256 (two accumulator stages must fit the 512 TMEM columns).
 // Big-M layers take the whole N in one tile (A streams from HBM exactly once); small-M layers (7x10 / 14x20
 // grids) split N so that the tile count approaches the SM count.
-int pick_bn(int M, int N) {
+int pick_bn(int M, int N, int nkb, bool three_x) {
+    // Cost model (SM cycles, calibrated on the device-side timelines in profiles/): a tile costs
+    //   nkb * max(MMA time, per-k-block pipeline latency) + epilogue + fixed, and the layer costs
+    //   ceil(tiles / SMs) tile times.  A (the activation tile) is re-read once per n-tile, so ties go to the wider tile.
     const int n16 = (N + 15) / 16 * 16;
     const int m_tiles = (M + BM - 1) / BM;
     const int sms = g_num_sms > 0 ? g_num_sms : 148;
-    if (n16 <= 256 && (m_tiles * 4 >= sms * 3 || n16 <= 64)) return n16;
-    for (int bn : {256, 192, 128, 96, 64}) {
-        if (bn > n16) continue;
-        if (m_tiles * ((n16 + bn - 1) / bn) * 4 >= sms * 3) return bn;
+    int best = 16;
+    double best_cost = 1e30;
+    for (int bn = 16; bn <= 256; bn += 16) {
+        if (bn > n16) break;
+        const size_t stage = (size_t)A_TILE_BYTES * (three_x ? 2 : 1) + (size_t)bn * 128 * (three_x ? 2 : 1);
+        const int stages = (int)((g_max_smem ? g_max_smem - 20000 : 210000) / stage);
+        if (stages < 3 && bn > 16) continue;
+        const int n_tiles = (n16 + bn - 1) / bn;
+        if (n_tiles > 1 && (bn % 32) != 0) continue;
+        const double mma = (three_x ? 3.0 : 1.0) * 4.0 * (bn / 2.0);       // 4 k-steps of 128 x bn x 8 per pass
+        const double lat = 2400.0 / (stages < 8 ? stages : 8);               // load->convert->mma->free round trip / depth
+        const double tile = nkb * (mma > lat ? mma : lat) + bn * 12.0 + 2500.0;
+        const double waste = (double)(n_tiles * bn) / n16;                   // zero-padded columns still cost MMA time
+        const long tiles = (long)m_tiles * n_tiles;
+        const double cost = (double)((tiles + sms - 1) / sms) * tile * (0.9 + 0.1 * waste) + n_tiles * 40.0;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
     }
-    return n16 < 64 ? n16 : 64;
+    return best;
 }
 
 int tc_init() {
@@ -564,10 +692,14 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.shift = a.shift;
     p.act = a.act;
     p.alpha = a.alpha;
+    p.act_slope = a.act == ACT_NONE ? 1.f : (a.act == ACT_LEAKY ? a.alpha : 0.f);
+    p.act_clamp = a.act == ACT_RELU6 ? 6.f : __int_as_float_host(0x7f800000);
     p.M = a.B * a.OH * a.OW;
     p.N = a.N;
     p.K = w.K;
-    p.BN = pick_bn(p.M, a.N);
+    p.three_x = (math_mode == K2Y_MATH_TC_3XTF32) ? 1 : 0;
+    p.nkb = w.Kpad / BK;
+    p.BN = pick_bn(p.M, a.N, p.nkb, p.three_x != 0);
     p.n_tiles = (w.Npad + p.BN - 1) / p.BN;
     p.m_tiles = (p.M + BM - 1) / BM;
     p.nkb = w.Kpad / BK;
@@ -576,7 +708,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
     p.tmem_cols = cols;
     const size_t stage_bytes = (size_t)A_TILE_BYTES * (p.three_x ? 2 : 1) + (size_t)p.BN * 128 * (p.three_x ? 2 : 1);
-    const size_t fixed = 1024 + sizeof(Barriers) + 64;
+    const size_t fixed = 1024 + sizeof(Barriers) + 1024 + 4 * 8192;  // alignment slack, barriers, epilogue staging (2 x 4 KB per warp)
     int stages = (int)((g_max_smem - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return cudaErrorInvalidConfiguration;
@@ -584,18 +716,49 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     const size_t smem = fixed + (size_t)stages * stage_bytes;
 
     const bool gather = !is_plain_1x1(a);
-    CUtensorMap map_a, map_bhi, map_blo;
+    CUtensorMap map_a, map_bhi, map_blo, map_out;
     memset(&map_a, 0, sizeof(map_a));
+    memset(&map_out, 0, sizeof(map_out));
+    p.tma_store = ((a.N & 3) == 0 && a.residual == nullptr && (((uintptr_t)a.dst) & 15) == 0) ? 1 : 0;
+    if (getenv("K2Y_TC_NO_TMA_STORE")) p.tma_store = 0;
+    if (p.tma_store && !make_map_2d(&map_out, a.dst, (uint64_t)p.M, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
     if (!gather && !make_map_2d(&map_a, a.src0, (uint64_t)p.M, (uint64_t)(a.C0 + a.C1), BM)) return cudaErrorInvalidValue;
     if (!make_map_2d(&map_bhi, w.d_hi, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
     if (!make_map_2d(&map_blo, w.d_lo, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
 
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    p.trace = nullptr;
+    p.dbg = getenv("K2Y_TC_DBG") ? atoi(getenv("K2Y_TC_DBG")) : 0;
+    const char *tr = getenv("K2Y_TC_TRACE");
+    long long *d_trace = nullptr;
+    if (tr && tr[0] == '1') {
+        cudaMalloc(&d_trace, (size_t)grid * 16 * sizeof(long long));
+        cudaMemset(d_trace, 0, (size_t)grid * 16 * sizeof(long long));
+        p.trace = d_trace;
+        fprintf(stderr, "[tc-trace] M=%d N=%d K=%d BN=%d tiles=%d (m %d x n %d) nkb=%d stages=%d grid=%d gather=%d 3x=%d smem=%zu\n", p.M,
+                p.N, p.K, p.BN, tiles, p.m_tiles, p.n_tiles, p.nkb, p.stages, grid, (int)gather, p.three_x, smem);
+    }
     if (gather)
-        conv_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+        conv_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, p);
     else
-        conv_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+        conv_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, p);
+    if (d_trace) {
+        cudaStreamSynchronize(st);
+        std::vector<long long> h((size_t)grid * 16);
+        cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        long long t0 = h[0];
+        for (int b = 0; b < grid; ++b)
+            if (h[(size_t)b * 16] && h[(size_t)b * 16] < t0) t0 = h[(size_t)b * 16];
+        static const char *names[13] = {"start", "setup_done", "tma_first", "tma_tile0_last", "mma_full_b0", "mma_conv0", "mma_tile0_commit",
+                                        "mma_all_issued", "epi_tile0_ready", "epi_tile0_done", "epi_all_done", "all_synced", "dealloc"};
+        for (int b : {0, grid / 2, grid - 1}) {
+            fprintf(stderr, "[tc-trace] cta %d:", b);
+            for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%.2fus", names[i], h[(size_t)b * 16 + i] ? (h[(size_t)b * 16 + i] - t0) * 1e-3 : -1.0);
+            fprintf(stderr, "\n");
+        }
+    }
     return cudaGetLastError();
 }
 

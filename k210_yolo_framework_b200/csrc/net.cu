@@ -72,7 +72,7 @@ struct k2y_net {
     std::vector<int> outputs;  // tensor ids
     std::map<std::string, int> auto_count;
     bool finalized = false, bound = false, keep_all = false, use_graph = true;
-    int math = K2Y_MATH_FP32_SIMT;
+    int math = K2Y_MATH_TC_3XTF32;  // default: tensor cores with fp32-class accuracy
     size_t arena_floats = 0;
     float *arena = nullptr;
     const float *x_dev = nullptr;
