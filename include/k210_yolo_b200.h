@@ -92,8 +92,9 @@ int k2y_net_predict_host(k2y_net *net, const float *x_host, int batch, float *co
 /* Kernel launches (graph nodes) one k2y_net_run(batch) issues. */
 int k2y_net_launches_per_run(const k2y_net *net, int *n);
 /* Measurement hooks (bench.py): one plain (non-graph) pass with a CUDA event between consecutive launches on
- * `stream`; ms_per_launch[i] = device time of launch i (n >= launches_per_run).  launch_info names launch i
+ * `stream`; ms_per_launch[i] = device time of schedule entry i (n >= schedule_len).  launch_info names launch i
  * (Keras layer name) and gives its algorithmic work per image: 2*MACs and fp32 activation bytes in+out. */
+int k2y_net_schedule_len(const k2y_net *net, int *n); /* layers in the schedule (a split-K layer is 2 kernels) */
 int k2y_net_profile(k2y_net *net, int batch, void *stream, float *ms_per_launch, int n);
 int k2y_net_launch_info(const k2y_net *net, int i, char *name, int name_len, double *flops_per_image,
                         double *bytes_per_image);

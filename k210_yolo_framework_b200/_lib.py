@@ -69,6 +69,7 @@ _SIGNATURES = {
     "k2y_net_run": (c_int, [c_void_p, c_int, c_void_p]),
     "k2y_net_predict_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_void_p), c_void_p]),
     "k2y_net_launches_per_run": (c_int, [c_void_p, POINTER(c_int)]),
+    "k2y_net_schedule_len": (c_int, [c_void_p, POINTER(c_int)]),
     "k2y_net_profile": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_float), c_int]),
     "k2y_net_launch_info": (c_int, [c_void_p, c_int, ctypes.c_char_p, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "k2y_net_set_keep_all": (c_int, [c_void_p, c_int]),

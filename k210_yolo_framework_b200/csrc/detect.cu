@@ -82,6 +82,29 @@ __device__ __forceinline__ float iou_yxyx(const float4 a, const float4 b) {
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
 }
 
+// `iou_yxyx(a, b) > thr` without the division in the common case: inter/uni > thr  <=>  inter > thr*uni (uni > 0).
+// The product form is only trusted outside a 1e-6 relative margin (>> the 3 roundings involved); inside it the
+// exact IEEE division decides, so the boolean is bit-identical to the reference's `iou > iou_threshold`.
+__device__ __forceinline__ bool iou_yxyx_gt(const float4 a, const float4 b, float thr) {
+    const float ymin_a = fminf(a.x, a.z), ymax_a = fmaxf(a.x, a.z);
+    const float xmin_a = fminf(a.y, a.w), xmax_a = fmaxf(a.y, a.w);
+    const float ymin_b = fminf(b.x, b.z), ymax_b = fmaxf(b.x, b.z);
+    const float xmin_b = fminf(b.y, b.w), xmax_b = fmaxf(b.y, b.w);
+    const float area_a = __fmul_rn(__fsub_rn(ymax_a, ymin_a), __fsub_rn(xmax_a, xmin_a));
+    const float area_b = __fmul_rn(__fsub_rn(ymax_b, ymin_b), __fsub_rn(xmax_b, xmin_b));
+    if (area_a <= 0.f || area_b <= 0.f) return 0.f > thr;
+    const float iy = fmaxf(__fsub_rn(fminf(ymax_a, ymax_b), fmaxf(ymin_a, ymin_b)), 0.f);
+    const float ix = fmaxf(__fsub_rn(fminf(xmax_a, xmax_b), fmaxf(xmin_a, xmin_b)), 0.f);
+    const float inter = __fmul_rn(iy, ix);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    if (thr >= 0.f && uni > 0.f) {
+        const float t = __fmul_rn(thr, uni);
+        if (inter > __fmul_rn(t, 1.000001f)) return true;
+        if (inter < __fmul_rn(t, 0.999999f)) return false;
+    }
+    return __fdiv_rn(inter, uni) > thr;
+}
+
 // region_layer.c box_iou on centre-form (x,y,w,h) boxes (:228-254).
 __device__ __forceinline__ float overlap_c(float x1, float w1, float x2, float w2) {
     const float l1 = __fsub_rn(x1, __fmul_rn(w1, 0.5f));
@@ -201,21 +224,35 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const Kera
     x.sc_y = __fdiv_rn(p.in_h, new_h);
     x.sc_x = __fdiv_rn(p.in_w, new_w);
 
-    // ---- scan: candidates of class c in index order ----
+    // ---- scan: candidates of class c in index order (4 x 32 boxes per step so that the loads overlap) ----
     int n = 0;
-    for (int base = 0; base < p.nbox; base += 32) {
-        const int box = base + lane;
-        bool pass = false;
-        float s = 0.f;
-        if (box < p.nbox) {
-            int l, a, col, row;
-            const float *e = box_entry(p, b, box, l, a, col, row);
-            s = __fmul_rn(sigmoidf_ref(__ldg(e + 5 + c)), sigmoidf_ref(__ldg(e + 4)));
-            pass = s >= p.obj;
+    for (int base = 0; base < p.nbox; base += 128) {
+        float lc[4], lk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int box = base + u * 32 + lane;
+            lc[u] = 0.f;
+            lk[u] = 0.f;
+            if (box < p.nbox) {
+                int l, a, col, row;
+                const float *e = box_entry(p, b, box, l, a, col, row);
+                lc[u] = __ldg(e + 4);
+                lk[u] = __ldg(e + 5 + c);
+            }
         }
-        const unsigned m = __ballot_sync(FULL, pass);
-        if (pass) keys[n + __popc(m & ((1u << lane) - 1u))] = pack_key(s, box);
-        n += __popc(m);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int box = base + u * 32 + lane;
+            bool pass = false;
+            float s = 0.f;
+            if (box < p.nbox) {
+                s = __fmul_rn(sigmoidf_ref(lk[u]), sigmoidf_ref(lc[u]));
+                pass = s >= p.obj;
+            }
+            const unsigned m = __ballot_sync(FULL, pass);
+            if (pass) keys[n + __popc(m & ((1u << lane) - 1u))] = pack_key(s, box);
+            n += __popc(m);
+        }
     }
     __syncwarp();
     unsigned long long rkey = 0ull;
@@ -231,49 +268,73 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const Kera
     }
 
     // ---- greedy NMS over the sorted candidates, 32 at a time ----
+    // Per chunk: (a) every lane tests ITS candidate against the boxes kept so far, (b) every lane computes the bitmask
+    // of later candidates of the chunk its box would suppress, (c) a short warp-uniform scan over the chunk resolves
+    // the greedy order from the masks.  The IoU work is thereby done 32-wide instead of one candidate at a time;
+    // the result is exactly the sequential algorithm's (a candidate is kept iff no earlier KEPT box overlaps it).
     k2y_det *out = p.dets + ((size_t)b * p.C + c) * p.maxk;
     float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f);  // lane s holds kept box s (first 32)
     int nsel = 0;
     for (int base = 0; base < n && nsel < p.maxk; base += 32) {
         const int i = base + lane;
         const unsigned long long mykey = (n <= 32) ? rkey : (i < n ? keys[i] : 0ull);
+        const int cnt = min(32, n - base);
         float4 cand = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) cand = decode_box(p, x, b, key_index(mykey));
-        const int cnt = min(32, n - base);
-        for (int j = 0; j < cnt && nsel < p.maxk; ++j) {
-            float4 cb;
-            cb.x = __shfl_sync(FULL, cand.x, j);
-            cb.y = __shfl_sync(FULL, cand.y, j);
-            cb.z = __shfl_sync(FULL, cand.z, j);
-            cb.w = __shfl_sync(FULL, cand.w, j);
-            const unsigned long long key = __shfl_sync(FULL, mykey, j);
-            bool sup = (lane < nsel) && (iou_yxyx(cb, mybox) > p.iou);
-            bool any = __ballot_sync(FULL, sup) != 0u;
-            for (int sb = 32; !any && sb < nsel; sb += 32) {  // only when max_per_class > 32
-                const int k = sb + lane;
-                sup = false;
-                if (k < nsel) {
-                    const k2y_det d = out[k];
-                    sup = iou_yxyx(cb, make_float4(d.ymin, d.xmin, d.ymax, d.xmax)) > p.iou;
-                }
-                any = __ballot_sync(FULL, sup) != 0u;
-            }
-            if (!any) {
-                if (lane == nsel) mybox = cb;
-                if (lane == 0) {
-                    k2y_det d;
-                    d.ymin = cb.x;
-                    d.xmin = cb.y;
-                    d.ymax = cb.z;
-                    d.xmax = cb.w;
-                    d.score = key_score(key);
-                    d.index = key_index(key);
-                    out[nsel] = d;
-                }
-                ++nsel;
-                __syncwarp();
-            }
+        // (a) against the kept set
+        bool dead = lane >= cnt;
+        const int nreg = min(nsel, 32);
+        for (int s2 = 0; s2 < nreg; ++s2) {
+            float4 kb;
+            kb.x = __shfl_sync(FULL, mybox.x, s2);
+            kb.y = __shfl_sync(FULL, mybox.y, s2);
+            kb.z = __shfl_sync(FULL, mybox.z, s2);
+            kb.w = __shfl_sync(FULL, mybox.w, s2);
+            if (!dead && iou_yxyx_gt(cand, kb, p.iou)) dead = true;
         }
+        for (int s2 = 32; s2 < nsel; ++s2) {  // only when max_per_class > 32
+            const k2y_det d = out[s2];
+            if (!dead && iou_yxyx_gt(cand, make_float4(d.ymin, d.xmin, d.ymax, d.xmax), p.iou)) dead = true;
+        }
+        // (b) suppression masks inside the chunk — only candidates that survived (a) can suppress anything,
+        //     so the loop runs over the set bits of `alive` (usually a handful) instead of all 32 lanes
+        const unsigned alive = ~__ballot_sync(FULL, dead);
+        unsigned mask = 0u;
+        for (unsigned mm = alive; mm; mm &= mm - 1u) {
+            const int j = __ffs(mm) - 1;
+            float4 ob;
+            ob.x = __shfl_sync(FULL, cand.x, j);
+            ob.y = __shfl_sync(FULL, cand.y, j);
+            ob.z = __shfl_sync(FULL, cand.z, j);
+            ob.w = __shfl_sync(FULL, cand.w, j);
+            if (j > lane && !dead && iou_yxyx_gt(ob, cand, p.iou)) mask |= 1u << j;
+        }
+        // (c) resolve in score order
+        unsigned remv = ~alive;
+        for (unsigned mm = alive; mm && nsel < p.maxk; mm &= mm - 1u) {
+            const int j = __ffs(mm) - 1;
+            if ((remv >> j) & 1u) continue;
+            float4 kb;
+            kb.x = __shfl_sync(FULL, cand.x, j);
+            kb.y = __shfl_sync(FULL, cand.y, j);
+            kb.z = __shfl_sync(FULL, cand.z, j);
+            kb.w = __shfl_sync(FULL, cand.w, j);
+            const unsigned long long key = __shfl_sync(FULL, mykey, j);
+            remv |= __shfl_sync(FULL, mask, j);
+            if (lane == nsel) mybox = kb;
+            if (lane == 0) {
+                k2y_det d;
+                d.ymin = kb.x;
+                d.xmin = kb.y;
+                d.ymax = kb.z;
+                d.xmax = kb.w;
+                d.score = key_score(key);
+                d.index = key_index(key);
+                out[nsel] = d;
+            }
+            ++nsel;
+        }
+        __syncwarp();
     }
     if (lane == 0) p.counts[b * p.C + c] = nsel;
 }

@@ -177,6 +177,7 @@ struct TcParams {
     float alpha;
     int M, N, K;
     int BN, n_tiles, m_tiles, nkb, stages;
+    int k_splits, kb_per_split;     // split-K: work item = (m-tile, n-tile, k-slice); partials go to a scratch buffer
     int three_x;                    // 1 = 3xTF32, 0 = single pass
     uint32_t tmem_cols;
     float act_slope, act_clamp;     // branch-free activation parameters
@@ -200,6 +201,8 @@ struct __align__(8) Barriers {
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_slot;
 };
+// dynamic smem besides the stage ring: alignment slack, barriers, epilogue staging (2 x 4 KB per epilogue warp)
+constexpr size_t FIXED_SMEM = 1024 + sizeof(Barriers) + 1024 + 4 * 8192;
 
 template <bool GATHER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -242,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = bars->tmem_slot;
     if (threadIdx.x == 0) K2Y_TRACE(1);
 
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
     auto stage_a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
     auto stage_a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES; };
     auto stage_b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES * (p.three_x ? 2u : 1u); };
@@ -255,16 +258,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t ph = 0;
             const uint32_t tx = b_bytes * (p.three_x ? 2u : 1u) + (GATHER ? 0u : (uint32_t)A_TILE_BYTES);
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                const int ks = t % p.k_splits, tt = t / p.k_splits;
+                const int mt = tt / p.n_tiles, nt = tt - mt * p.n_tiles;
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
                     const uint32_t fb = smem_u32(&bars->full_b[s]);
                     mbar_arrive_expect_tx(fb, tx);
                     if (!GATHER) tma_load_2d(stage_a_hi(s), &map_a, fb, kb * BK, mt * BM);
                     tma_load_2d(stage_b_hi(s), &map_bhi, fb, kb * BK, nt * p.BN);
                     if (p.three_x) tma_load_2d(stage_b_lo(s), &map_blo, fb, kb * BK, nt * p.BN);
-                    if (t == (int)blockIdx.x && kb == 0) K2Y_TRACE(2);
-                    if (t == (int)blockIdx.x && kb == p.nkb - 1) K2Y_TRACE(3);
+                    if (t == (int)blockIdx.x && kb == kb0) K2Y_TRACE(2);
+                    if (t == (int)blockIdx.x && kb == kb1 - 1) K2Y_TRACE(3);
                     if (++s == p.stages) {
                         s = 0;
                         ph ^= 1u;
@@ -283,11 +288,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(smem_u32(&bars->tmem_empty[a]), aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d = tmem_base + a * (uint32_t)p.BN;
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                const int ks = t % p.k_splits;
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&bars->full_b[s]), ph);
-                    if (t == (int)blockIdx.x && kb == 0) K2Y_TRACE(4);
+                    if (t == (int)blockIdx.x && kb == kb0) K2Y_TRACE(4);
                     if (use_conv) mbar_wait(smem_u32(&bars->conv[s]), ph);
-                    if (t == (int)blockIdx.x && kb == 0) K2Y_TRACE(5);
+                    if (t == (int)blockIdx.x && kb == kb0) K2Y_TRACE(5);
                     tc_fence_after();
                     const uint64_t a_hi = make_desc_sw128(stage_a_hi(s)), b_hi = make_desc_sw128(stage_b_hi(s));
                     const uint64_t a_lo = make_desc_sw128(stage_a_lo(s)), b_lo = make_desc_sw128(stage_b_lo(s));
@@ -296,11 +303,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
                         if (p.three_x) {
                             // small terms first, then the dominant hi*hi
-                            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, (kb | kk) != 0);
+                            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, ((kb - kb0) | kk) != 0);
                             umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
                             umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
                         } else {
-                            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, (kb | kk) != 0);
+                            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, ((kb - kb0) | kk) != 0);
                         }
                     }
                     umma_commit(smem_u32(&bars->empty[s]));  // frees the smem slot when these MMAs retire
@@ -322,7 +329,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int s = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int mt = t / p.n_tiles;
+                const int ks = t % p.k_splits, tt = t / p.k_splits;
+                const int mt = tt / p.n_tiles;
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 const int m = mt * BM + r;
                 int b = -1, iy0 = 0, ix0 = 0;
                 if (m < p.M) {
@@ -333,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     iy0 = oy * p.stride - p.pad_t;
                     ix0 = ox * p.stride - p.pad_l;
                 }
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     // a k-block = 32 consecutive channels of ONE tap of ONE source (Cin % 32 == 0, C0 % 32 == 0)
                     const int k = kb * BK;
                     const int tap = k / Cin;
@@ -372,7 +381,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int s = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                const int ks = t % p.k_splits;
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(GATHER ? &bars->full_a[s] : &bars->full_b[s]), ph);
                     if (p.three_x && !(p.dbg & 4)) {
                         float4 *hi = reinterpret_cast<float4 *>(smem_gen + (size_t)s * stage_bytes);
@@ -416,13 +427,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int chunk = lane & 7, rsub = lane >> 3;
         uint32_t acc_it = 0, stg_it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
-            const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+            const int ks = t % p.k_splits, tt = t / p.k_splits;
+            const int mt = tt / p.n_tiles, nt = tt - mt * p.n_tiles;
             const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+            // pull this tile's scale/shift lines into L1 while the mainloop is still running
+            if (lane * 32 < p.BN && nt * p.BN + lane * 32 < p.N) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scale + nt * p.BN + lane * 32));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.shift + nt * p.BN + lane * 32));
+            }
             mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
             if (t == (int)blockIdx.x && threadIdx.x == 10 * 32) K2Y_TRACE(8);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)p.BN;
-            const int m_base = mt * BM + q * 32;
+            // split-K partials of slice ks live at rows [ks * m_tiles * 128, ...) of the scratch tensor
+            const int m_base = (ks * p.m_tiles + mt) * BM + q * 32;
             for (int c0 = 0; c0 < p.BN; c0 += 32, ++stg_it) {
                 const int ncols = (p.BN - c0) < 32 ? (p.BN - c0) : 32;  // 32 or 16
                 const int n0 = nt * p.BN + c0;
@@ -525,6 +543,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// Split-K reduction + epilogue: out[m,n] = act(scale[n] * sum_s partial[s][m][n] + shift[n]) (+ residual).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restrict__ part, float *__restrict__ dst,
+                                                            const float *__restrict__ residual, const float *__restrict__ scale,
+                                                            const float *__restrict__ shift, int M, int N, int splits,
+                                                            size_t split_stride, float slope, float clamp) {
+    const int n4 = N >> 2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)M * n4) return;
+    const int n = (int)(idx % n4) * 4;
+    const size_t m = idx / n4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(part + (size_t)s * split_stride + m * N + n));
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + n));
+    const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + n));
+    float4 o;
+    o.x = act_bf(fmaf(acc.x, sc.x, sh.x), slope, clamp);
+    o.y = act_bf(fmaf(acc.y, sc.y, sh.y), slope, clamp);
+    o.z = act_bf(fmaf(acc.z, sc.z, sh.z), slope, clamp);
+    o.w = act_bf(fmaf(acc.w, sc.w, sh.w), slope, clamp);
+    if (residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4 *>(residual + m * N + n));
+        o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+    }
+    *reinterpret_cast<float4 *>(dst + m * N + n) = o;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -574,40 +621,60 @@ float tf32_rna_host(float x) {
     return y;
 }
 
-int g_num_sms = 0;
-size_t g_max_smem = 0;
+
 
 // Tile width: UMMA_N is a multiple of 16 and <= 256 (two accumulator stages must fit the 512 TMEM columns).
 // Big-M layers take the whole N in one tile (A streams from HBM exactly once); small-M layers (7x10 / 14x20
 // grids) split N so that the tile count approaches the SM count.
-int pick_bn(int M, int N, int nkb, bool three_x) {
-    // Cost model (SM cycles, calibrated on the device-side timelines in profiles/): a tile costs
-    //   nkb * max(MMA time, per-k-block pipeline latency) + epilogue + fixed, and the layer costs
-    //   ceil(tiles / SMs) tile times.  A (the activation tile) is re-read once per n-tile, so ties go to the wider tile.
+int g_num_sms = 0;
+size_t g_max_smem = 0;
+float *g_scratch = nullptr;      // split-K partials [splits][m_tiles*128][N]
+size_t g_scratch_bytes = 0;
+float *g_ones = nullptr, *g_zeros = nullptr;  // identity scale / shift for the partial pass
+constexpr int ID_LEN = 4096;
+
+// Tile width BN and split-K factor from a small cost model (SM cycles, calibrated on the device-side timelines
+// in profiles/): a work item costs  kb * max(MMA time, pipeline latency / depth) + epilogue + fixed,  the layer costs
+// ceil(items / SMs) item times (+ the reduction pass when K is split).  A is re-read once per n-tile, so ties go to
+// the wider tile; BN is a multiple of 32 when N is tiled (TMA-store boxes are 32 columns wide).
+void pick_tile(int M, int N, int nkb, bool three_x, int *bn_out, int *splits_out) {
     const int n16 = (N + 15) / 16 * 16;
     const int m_tiles = (M + BM - 1) / BM;
     const int sms = g_num_sms > 0 ? g_num_sms : 148;
-    int best = 16;
+    const char *force = getenv("K2Y_TC_SPLITK");
+    int best = 16, best_s = 1;
     double best_cost = 1e30;
     for (int bn = 16; bn <= 256; bn += 16) {
         if (bn > n16) break;
         const size_t stage = (size_t)A_TILE_BYTES * (three_x ? 2 : 1) + (size_t)bn * 128 * (three_x ? 2 : 1);
-        const int stages = (int)((g_max_smem ? g_max_smem - 20000 : 210000) / stage);
+        const int stages = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage);
         if (stages < 3 && bn > 16) continue;
         const int n_tiles = (n16 + bn - 1) / bn;
         if (n_tiles > 1 && (bn % 32) != 0) continue;
         const double mma = (three_x ? 3.0 : 1.0) * 4.0 * (bn / 2.0);       // 4 k-steps of 128 x bn x 8 per pass
-        const double lat = 2400.0 / (stages < 8 ? stages : 8);               // load->convert->mma->free round trip / depth
-        const double tile = nkb * (mma > lat ? mma : lat) + bn * 12.0 + 2500.0;
+        const double lat = 4400.0 / (stages < 8 ? stages : 8);               // load->convert->mma->free round trip / depth
+        const double kbt = mma > lat ? mma : lat;
         const double waste = (double)(n_tiles * bn) / n16;                   // zero-padded columns still cost MMA time
-        const long tiles = (long)m_tiles * n_tiles;
-        const double cost = (double)((tiles + sms - 1) / sms) * tile * (0.9 + 0.1 * waste) + n_tiles * 40.0;
-        if (cost < best_cost) {
-            best_cost = cost;
-            best = bn;
+        for (int sp = 1; sp <= 8; ++sp) {
+            if (force && sp != atoi(force) && !(atoi(force) < 1 && sp == 1)) continue;
+            if (sp > 1) {
+                if ((N & 3) != 0 || N > ID_LEN || nkb / sp < 12) continue;
+                if ((size_t)sp * m_tiles * BM * N * sizeof(float) > g_scratch_bytes) continue;
+            }
+            const int kb = (nkb + sp - 1) / sp;
+            const long items = (long)m_tiles * n_tiles * sp;
+            const double item = kb * kbt + bn * 12.0 + 2500.0;
+            double cost = (double)((items + sms - 1) / sms) * item * (0.9 + 0.1 * waste) + n_tiles * 40.0;
+            if (sp > 1) cost += 7000.0 + (double)sp * M * N * 4.0 / 1500.0;  // reduce pass: launch + partial traffic
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = bn;
+                best_s = sp;
+            }
         }
     }
-    return best;
+    *bn_out = best;
+    *splits_out = best_s;
 }
 
 int tc_init() {
@@ -622,6 +689,13 @@ int tc_init() {
                                         (int)prop.sharedMemPerBlockOptin));
     g_max_smem = prop.sharedMemPerBlockOptin;
     g_num_sms = prop.multiProcessorCount;
+    g_scratch_bytes = (size_t)64 << 20;
+    K2Y_CUDA_CHECK(cudaMalloc(&g_scratch, g_scratch_bytes));
+    K2Y_CUDA_CHECK(cudaMalloc(&g_ones, ID_LEN * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMalloc(&g_zeros, ID_LEN * sizeof(float)));
+    std::vector<float> ones(ID_LEN, 1.f);
+    K2Y_CUDA_CHECK(cudaMemcpy(g_ones, ones.data(), ID_LEN * sizeof(float), cudaMemcpyHostToDevice));
+    K2Y_CUDA_CHECK(cudaMemset(g_zeros, 0, ID_LEN * sizeof(float)));
     return K2Y_OK;
 }
 
@@ -699,16 +773,16 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.K = w.K;
     p.three_x = (math_mode == K2Y_MATH_TC_3XTF32) ? 1 : 0;
     p.nkb = w.Kpad / BK;
-    p.BN = pick_bn(p.M, a.N, p.nkb, p.three_x != 0);
+    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, &p.BN, &p.k_splits);
     p.n_tiles = (w.Npad + p.BN - 1) / p.BN;
     p.m_tiles = (p.M + BM - 1) / BM;
-    p.nkb = w.Kpad / BK;
-    p.three_x = (math_mode == K2Y_MATH_TC_3XTF32) ? 1 : 0;
+    p.kb_per_split = (p.nkb + p.k_splits - 1) / p.k_splits;
+    p.k_splits = (p.nkb + p.kb_per_split - 1) / p.kb_per_split;  // no empty slices
     uint32_t cols = 32;
     while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
     p.tmem_cols = cols;
     const size_t stage_bytes = (size_t)A_TILE_BYTES * (p.three_x ? 2 : 1) + (size_t)p.BN * 128 * (p.three_x ? 2 : 1);
-    const size_t fixed = 1024 + sizeof(Barriers) + 1024 + 4 * 8192;  // alignment slack, barriers, epilogue staging (2 x 4 KB per warp)
+    const size_t fixed = FIXED_SMEM;
     int stages = (int)((g_max_smem - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return cudaErrorInvalidConfiguration;
@@ -720,13 +794,26 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     memset(&map_a, 0, sizeof(map_a));
     memset(&map_out, 0, sizeof(map_out));
     p.tma_store = ((a.N & 3) == 0 && a.residual == nullptr && (((uintptr_t)a.dst) & 15) == 0) ? 1 : 0;
-    if (getenv("K2Y_TC_NO_TMA_STORE")) p.tma_store = 0;
-    if (p.tma_store && !make_map_2d(&map_out, a.dst, (uint64_t)p.M, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
+    if (getenv("K2Y_TC_NO_TMA_STORE") && p.k_splits == 1) p.tma_store = 0;
+    const size_t mpad = (size_t)p.m_tiles * BM;
+    if (p.k_splits > 1) {
+        // partial pass: raw accumulators -> scratch through the TMA-store epilogue (identity scale, no activation)
+        p.tma_store = 1;
+        p.dst = g_scratch;
+        p.residual = nullptr;
+        p.scale = g_ones;
+        p.shift = g_zeros;
+        p.act_slope = 1.f;
+        p.act_clamp = __int_as_float_host(0x7f800000);
+        if (!make_map_2d(&map_out, g_scratch, (uint64_t)p.k_splits * mpad, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
+    } else if (p.tma_store && !make_map_2d(&map_out, a.dst, (uint64_t)p.M, (uint64_t)a.N, 32)) {
+        return cudaErrorInvalidValue;
+    }
     if (!gather && !make_map_2d(&map_a, a.src0, (uint64_t)p.M, (uint64_t)(a.C0 + a.C1), BM)) return cudaErrorInvalidValue;
     if (!make_map_2d(&map_bhi, w.d_hi, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
     if (!make_map_2d(&map_blo, w.d_lo, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
 
-    const int tiles = p.m_tiles * p.n_tiles;
+    const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     p.trace = nullptr;
     p.dbg = getenv("K2Y_TC_DBG") ? atoi(getenv("K2Y_TC_DBG")) : 0;
@@ -736,8 +823,8 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         cudaMalloc(&d_trace, (size_t)grid * 16 * sizeof(long long));
         cudaMemset(d_trace, 0, (size_t)grid * 16 * sizeof(long long));
         p.trace = d_trace;
-        fprintf(stderr, "[tc-trace] M=%d N=%d K=%d BN=%d tiles=%d (m %d x n %d) nkb=%d stages=%d grid=%d gather=%d 3x=%d smem=%zu\n", p.M,
-                p.N, p.K, p.BN, tiles, p.m_tiles, p.n_tiles, p.nkb, p.stages, grid, (int)gather, p.three_x, smem);
+        fprintf(stderr, "[tc-trace] M=%d N=%d K=%d BN=%d tiles=%d (m %d x n %d x k %d) nkb=%d stages=%d grid=%d gather=%d 3x=%d smem=%zu\n", p.M,
+                p.N, p.K, p.BN, tiles, p.m_tiles, p.n_tiles, p.k_splits, p.nkb, p.stages, grid, (int)gather, p.three_x, smem);
     }
     if (gather)
         conv_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, p);
@@ -759,7 +846,23 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
             fprintf(stderr, "\n");
         }
     }
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (p.k_splits > 1) {
+        const float slope = a.act == ACT_NONE ? 1.f : (a.act == ACT_LEAKY ? a.alpha : 0.f);
+        const float clamp = a.act == ACT_RELU6 ? 6.f : __int_as_float_host(0x7f800000);
+        const size_t total = (size_t)p.M * (a.N / 4);
+        splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g_scratch, a.dst, a.residual, a.scale, a.shift, p.M, a.N,
+                                                                            p.k_splits, mpad * a.N, slope, clamp);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode) {
+    int bn = 0, splits = 1;
+    pick_tile(a.B * a.OH * a.OW, a.N, w.Kpad / BK, math_mode == K2Y_MATH_TC_3XTF32, &bn, &splits);
+    return splits > 1 ? 2 : 1;
 }
 
 }  // namespace k2y

@@ -15,6 +15,7 @@ struct TcWeights {
 int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N);  // kernel_kn: [K][N] row-major (Keras HWIO flattened)
 void tc_free(TcWeights &w);
 bool tc_supported(const ConvArgs &a, const TcWeights &w);
+int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode);  // kernels one launch_conv_tc issues
 cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st);
 
 }  // namespace k2y

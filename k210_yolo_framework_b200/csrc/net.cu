@@ -79,6 +79,7 @@ struct k2y_net {
     std::vector<float *> heads_dev;
     std::map<int, cudaGraphExec_t> graphs;
     int last_batch = 0;
+    int launches = 0;  // kernels issued by the last issue_layers() pass
 
     std::string auto_name(const std::string &base) {
         int n = auto_count[base]++;
@@ -384,6 +385,7 @@ int check_net(const k2y_net *n, const char *fn) {
 
 int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullptr) {
     int li = 0;
+    n->launches = 0;
     if (ev) cudaEventRecord(ev[0], st);
     for (Layer &L : n->layers) {
         const Tensor &s0 = n->tensors[L.src0];
@@ -416,8 +418,10 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
             a.alpha = L.alpha;
             if (n->math != K2Y_MATH_FP32_SIMT && tc_supported(a, L.tc)) {
                 e = launch_conv_tc(a, L.tc, n->math, st);
+                n->launches += tc_launch_count(a, L.tc, n->math);
             } else {
                 e = launch_conv_simt(a, st);
+                n->launches += 1;
             }
         } else if (L.kind == L_DW) {
             DwArgs a;
@@ -438,6 +442,7 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
             a.act = L.act;
             a.alpha = L.alpha;
             e = launch_dwconv(a, st);
+            n->launches += 1;
         } else {
             PoolArgs a;
             a.src = tensor_ptr(n, L.src0);
@@ -450,6 +455,7 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
             a.OW = d.w;
             a.stride = L.stride;
             e = launch_maxpool(a, st);
+            n->launches += 1;
         }
         if (e != cudaSuccess) {
             set_error("layer %s: launch failed: %s", L.name.c_str(), cudaGetErrorString(e));
@@ -817,7 +823,7 @@ extern "C" int k2y_net_predict_host(k2y_net *net, const float *x_host, int batch
 
 extern "C" int k2y_net_launches_per_run(const k2y_net *net, int *n) {
     if (check_net(net, "k2y_net_launches_per_run") || !n) return K2Y_ERR_INVALID;
-    *n = (int)net->layers.size();
+    *n = net->launches > 0 ? net->launches : (int)net->layers.size();  // exact after the first run (split-K adds reducers)
     return K2Y_OK;
 }
 
@@ -845,6 +851,12 @@ extern "C" int k2y_net_read_layer(k2y_net *net, const char *name, int batch, flo
     }
     set_error("k2y_net_read_layer: no layer named '%s'", name);
     return K2Y_ERR_INVALID;
+}
+
+extern "C" int k2y_net_schedule_len(const k2y_net *net, int *n) {
+    if (check_net(net, "k2y_net_schedule_len") || !n) return K2Y_ERR_INVALID;
+    *n = (int)net->layers.size();
+    return K2Y_OK;
 }
 
 extern "C" int k2y_net_profile(k2y_net *net, int batch, void *stream, float *ms_per_launch, int n) {

@@ -36,6 +36,15 @@ class DetectionPipeline:
         self._img_hw = torch.tensor([[image_size[0], image_size[1]]] * batch, dtype=torch.float32, device=dev)
         self._host_dets = torch.empty(self.gather.dets.shape, dtype=torch.int32).pin_memory()
         self._host_counts = torch.empty(self.gather.counts.shape, dtype=torch.int32).pin_memory()
+        # streaming mode (submit / collect): two staging slots so that the H2D copy of batch i+1 overlaps batch i
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = [torch.empty_like(self.engine.input_buffer) for _ in range(2)]
+        self._slot_dets = [torch.empty(self.gather.dets.shape, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._slot_counts = [torch.empty(self.gather.counts.shape, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self._stage_free = [torch.cuda.Event() for _ in range(2)]
+        self._d2h_done = [torch.cuda.Event() for _ in range(2)]
+        self._submitted = 0
 
     def set_image_shapes(self, image_hw) -> None:
         """Original (pre-letterbox) image sizes, [batch, 2] (h, w); defaults to the network input size."""
@@ -60,6 +69,33 @@ class DetectionPipeline:
         self._host_counts.copy_(counts, non_blocking=True)
         torch.cuda.current_stream(self.device_index).synchronize()
         return self._host_dets, self._host_counts
+
+    def submit(self, x_host: torch.Tensor) -> int:
+        """Streaming form of ``detect_host``: enqueue one batch (pinned host float32 [n,H,W,3]) and return a ticket.
+        The H2D copy runs on a side stream into a staging slot, so it overlaps the previous batch's kernels; at
+        most two batches are in flight — ``collect`` the ticket of batch i-1 before submitting batch i+1."""
+        n = x_host.shape[0]
+        slot = self._submitted % 2
+        self._submitted += 1
+        compute = torch.cuda.current_stream(self.device_index)
+        self._copy_stream.wait_event(self._stage_free[slot])
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[slot][:n].copy_(x_host, non_blocking=True)
+            self._h2d_done[slot].record(self._copy_stream)
+        compute.wait_event(self._h2d_done[slot])
+        self.engine.input_buffer[:n].copy_(self._stage[slot][:n], non_blocking=True)
+        self._stage_free[slot].record(compute)
+        dets, counts = self.step_device(n)
+        self._slot_dets[slot].copy_(dets, non_blocking=True)
+        self._slot_counts[slot].copy_(counts, non_blocking=True)
+        self._d2h_done[slot].record(compute)
+        return slot
+
+    def collect(self, ticket: int):
+        """Blocks until the batch behind `ticket` is on the host; returns (dets, counts) pinned host tensors (valid
+        until the ticket's slot is reused two submits later)."""
+        self._d2h_done[ticket].synchronize()
+        return self._slot_dets[ticket], self._slot_counts[ticket]
 
     def launches_per_step(self) -> int:
         return self.engine.launches_per_run() + 1  # + the fused decode/NMS kernel

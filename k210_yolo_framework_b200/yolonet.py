@@ -211,7 +211,9 @@ class YoloEngine:
     def profile(self, batch: int) -> List[dict]:
         """One event-instrumented pass: [{name, ms, flops, bytes}] per launch (flops/bytes for `batch` images)."""
         self._bind()
-        n = self.launches_per_run()
+        cnt = ctypes.c_int()
+        check(lib.k2y_net_schedule_len(self._h, ctypes.byref(cnt)))
+        n = cnt.value
         ms = (ctypes.c_float * n)()
         st = torch.cuda.current_stream(self.device_index)
         check(lib.k2y_net_profile(self._h, int(batch), ctypes.c_void_p(st.cuda_stream), ms, n))

@@ -112,3 +112,24 @@ def test_unsupported_shape_is_reported():
     kernel = np.zeros((3, 3, 3, 16), np.float32)
     with pytest.raises(_lib.K2YError):
         _run(x0, None, None, kernel, np.ones(16), np.zeros(16), 0, 3, 1, 0, 0, 0.0, _lib.MATH_TC_3XTF32)
+
+
+@pytest.mark.parametrize("splits", [2, 4, 7])
+def test_split_k_matches_reference(splits, monkeypatch):
+    """Deep-K 3x3 convs split their K range over several CTAs (partials through the TMA-store epilogue + reduce pass)."""
+    monkeypatch.setenv("K2Y_TC_SPLITK", str(splits))
+    for shape in (SHAPES[6], SHAPES[7], SHAPES[9]):
+        B, H, W, C0, C1, up0, Cout, k, stride, pad_mode, act, use_res = shape
+        rng = np.random.default_rng(splits)
+        x0 = rng.normal(0, 1, (B, H, W, C0)).astype(np.float32)
+        hh, ww = (H * 2, W * 2) if up0 else (H, W)
+        x1 = rng.normal(0, 1, (B, hh, ww, C1)).astype(np.float32) if C1 else None
+        kernel = (rng.normal(0, 1, (k, k, C0 + C1, Cout)) / np.sqrt(k * k * (C0 + C1))).astype(np.float32)
+        scale = rng.uniform(0.5, 2.0, Cout).astype(np.float32)
+        shift = rng.normal(0, 0.5, Cout).astype(np.float32)
+        ref0 = _ref(x0, x1, None, kernel, scale, shift, up0, k, stride, pad_mode, act, 0.1)
+        res = rng.normal(0, 1, ref0.shape).astype(np.float32) if use_res else None
+        ref = _ref(x0, x1, res, kernel, scale, shift, up0, k, stride, pad_mode, act, 0.1)
+        got = _run(x0, x1, res, kernel, scale, shift, up0, k, stride, pad_mode, act, 0.1, _lib.MATH_TC_3XTF32)
+        assert np.isfinite(got).all()
+        assert np.abs(got - ref).max() < 2e-4, f"splits={splits} shape={shape}: {np.abs(got - ref).max():.3e}"

@@ -86,9 +86,9 @@ def test_device_api_graph_replay_and_batching():
     b = [t.clone() for t in m.predict_device(x)]          # replays it
     for p, q in zip(a, b):
         assert torch.equal(p, q)
-    c = [t.clone() for t in m.predict_device(x[1:3])]     # different batch -> second graph
-    for p, q in zip(a, c):
-        assert torch.equal(p[1:3], q)
+    c = [t.clone() for t in m.predict_device(x[1:3])]     # different batch -> second graph; tile / split-K shapes may
+    for p, q in zip(a, c):                                 # differ with M, so only the accumulation order changes
+        assert torch.allclose(p[1:3], q, atol=2e-4, rtol=1e-4)
     m.engine.set_use_graph(False)
     d = m.predict_device(x)
     for p, q in zip(a, d):
@@ -96,7 +96,7 @@ def test_device_api_graph_replay_and_batching():
     host = m.predict(x.cpu().numpy())
     for p, q in zip(a, host):
         np.testing.assert_array_equal(p.cpu().numpy(), q)
-    assert m.engine.launches_per_run() == 32
+    assert m.engine.launches_per_run() >= 32   # + split-K reducers
 
 
 def test_errors():
