@@ -213,6 +213,8 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    # keep stdout to the single JSON line: NCCL's version banner / debug log goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     math_mode = {"fp32_simt": _lib.MATH_FP32_SIMT, "tc_3xtf32": _lib.MATH_TC_3XTF32, "tc_tf32": _lib.MATH_TC_TF32}[args.math]
