@@ -28,6 +28,7 @@ extern "C" {
 #define K2Y_MATH_FP32_SIMT 0   /* fp32 FFMA on CUDA cores (exact-order reference path on the GPU) */
 #define K2Y_MATH_TC_3XTF32 1   /* tcgen05 kind::tf32, hi/lo split x3 (fp32-class accuracy) */
 #define K2Y_MATH_TC_TF32 2     /* tcgen05 kind::tf32, single pass */
+#define K2Y_MATH_TC_BF16X3 3   /* tcgen05 kind::f16: fp32 operands split into (hi, mid) bf16 planes, 3 MMAs (~16-bit mantissa) */
 
 const char *k2y_last_error(void);
 int k2y_version(void);

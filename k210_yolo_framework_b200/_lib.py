@@ -17,7 +17,8 @@ K2Y_OK = 0
 MATH_FP32_SIMT = 0
 MATH_TC_3XTF32 = 1
 MATH_TC_TF32 = 2
-MATH_NAMES = {MATH_FP32_SIMT: "fp32_simt", MATH_TC_3XTF32: "tc_3xtf32", MATH_TC_TF32: "tc_tf32"}
+MATH_TC_BF16X3 = 3
+MATH_NAMES = {MATH_FP32_SIMT: "fp32_simt", MATH_TC_3XTF32: "tc_3xtf32", MATH_TC_TF32: "tc_tf32", MATH_TC_BF16X3: "tc_bf16x3"}
 
 
 class K2YError(RuntimeError):

@@ -67,6 +67,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// One lane of a CONVERGED warp.  Issuing the async instructions (TMA, tcgen05.mma/commit) under elect.sync inside
+// warp-uniform control flow lets ptxas keep descriptors and addresses in uniform registers; under `if (lane == 0)` every
+// operand went through R2UR and an MMA issue cost ~115 cycles regardless of its shape (profiles/ timelines).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -77,6 +91,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -105,8 +135,45 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (lane = row, 8 columns = one tf32 k-step)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -165,6 +232,24 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// D = F32, A = B = BF16 (kind::f16), K-major B, dense.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// fp32 -> bf16 bits, round to nearest even (finite inputs)
+__device__ __forceinline__ uint32_t bf16_rne_bits(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+
+// two fp32 -> packed bf16x2 (round to nearest even): lo element in bits [0,16), hi element in [16,32)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+
 struct TcParams {
     // gather-mode A source (also used for the shape arithmetic in both modes)
     const float *src0, *src1;
@@ -177,8 +262,11 @@ struct TcParams {
     float alpha;
     int M, N, K;
     int BN, n_tiles, m_tiles, nkb, stages;
+    int cluster;                    // 1, or 2: CTA pairs on adjacent m-tiles share every weight tile through TMA multicast
     int k_splits, kb_per_split;     // split-K: work item = (m-tile, n-tile, k-slice); partials go to a scratch buffer
-    int three_x;                    // 1 = 3xTF32, 0 = single pass
+    int three_x;                    // 1 = split scheme (3 MMAs per k-step: lo*hi + hi*lo + hi*hi), 0 = single pass
+    int bf16;                       // 1 = bf16x3: operands are bf16 (hi, mid) planes, 64 k per k-block; 0 = tf32, 32 k per k-block
+    int a_boxes;                    // 16 KB sub-tiles of raw fp32 A per stage (k per k-block / 32)
     uint32_t tmem_cols;
     float act_slope, act_clamp;     // branch-free activation parameters
     int tma_store;                  // 1: epilogue writes through a TMA store (N % 4 == 0, no residual)
@@ -193,7 +281,7 @@ __device__ __forceinline__ long long gtime() {
 }
 #define K2Y_TRACE(slot)                                                                  \
     do {                                                                                 \
-        if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtime();                \
+        if (p.trace) p.trace[(size_t)blockIdx.x * 64 + (slot)] = gtime();                \
     } while (0)
 
 struct __align__(8) Barriers {
@@ -202,7 +290,7 @@ struct __align__(8) Barriers {
     uint32_t tmem_slot;
 };
 // dynamic smem besides the stage ring: alignment slack, barriers, epilogue staging (2 x 4 KB per epilogue warp)
-constexpr size_t FIXED_SMEM = 1024 + sizeof(Barriers) + 1024 + 4 * 8192;
+constexpr size_t FIXED_SMEM = 1024 + sizeof(Barriers) + 1024 + 4 * 8192 + 4096;  // + double-buffered scale/shift of a tile
 
 template <bool GATHER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -213,12 +301,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // carve: [stages] x { A_hi(raw) 16K | A_lo 16K (3x) | B_hi BN*128 | B_lo BN*128 (3x) }, then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-    const uint32_t stage_bytes = (uint32_t)A_TILE_BYTES * (p.three_x ? 2u : 1u) + b_bytes * (p.three_x ? 2u : 1u);
+    // 3xTF32: the converter writes the hi/lo planes of A into TENSOR MEMORY (the MMA reads A from TMEM), so shared
+    // memory only holds the raw fp32 A tile and the two weight planes — shared-memory bandwidth was the limiter when
+    // all three MMAs of a k-step streamed A from smem.
+    const uint32_t a_bytes = (uint32_t)A_TILE_BYTES * (uint32_t)p.a_boxes;
+    const uint32_t stage_bytes = a_bytes + b_bytes * (p.three_x ? 2u : 1u);
+    const int KBK = p.a_boxes * BK;  // k values per k-block
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     Barriers *bars = reinterpret_cast<Barriers *>(smem_gen + (size_t)p.stages * stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool use_conv = p.three_x || GATHER;
+    const int crank = p.cluster == 2 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = (int)blockIdx.x / p.cluster, num_clusters = (int)gridDim.x / p.cluster;
 
     if (threadIdx.x == 0) {
         K2Y_TRACE(0);
@@ -226,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(smem_u32(&bars->full_b[s]), 1);
             mbar_init(smem_u32(&bars->full_a[s]), 128);
             mbar_init(smem_u32(&bars->conv[s]), 128);
-            mbar_init(smem_u32(&bars->empty[s]), 1);
+            mbar_init(smem_u32(&bars->empty[s]), (uint32_t)p.cluster);  // every MMA of the cluster must retire the stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&bars->tmem_full[a]), 1);
@@ -240,36 +335,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_slot), p.tmem_cols);
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster == 2) cluster_sync_all();  // peer barriers are initialised before any multicast can reach them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_slot;
     if (threadIdx.x == 0) K2Y_TRACE(1);
 
-    const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+    const int mp_tiles = (p.m_tiles + p.cluster - 1) / p.cluster;
+    const int num_tiles = mp_tiles * p.n_tiles * p.k_splits;   // work items per cluster sequence
     auto stage_a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
-    auto stage_a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES; };
-    auto stage_b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES * (p.three_x ? 2u : 1u); };
+    auto stage_b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + a_bytes; };
+    // tensor-memory columns: [0, 2*BN) two accumulators, then per stage 32 columns of A_hi and 32 of A_lo
+    auto tmem_a_hi = [&](int s) { return tmem_base + 2u * (uint32_t)p.BN + (uint32_t)s * 64u; };
     auto stage_b_lo = [&](int s) { return stage_b_hi(s) + b_bytes; };
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
+        {
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t tx = b_bytes * (p.three_x ? 2u : 1u) + (GATHER ? 0u : (uint32_t)A_TILE_BYTES);
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const uint32_t tx = b_bytes * (p.three_x ? 2u : 1u) + (GATHER ? 0u : a_bytes);
+            const int bk_elems = p.bf16 ? 64 : 32;  // k-block extent in elements of the weight map (bf16 or fp32)
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
                 const int ks = t % p.k_splits, tt = t / p.k_splits;
-                const int mt = tt / p.n_tiles, nt = tt - mt * p.n_tiles;
+                const int mp = tt / p.n_tiles, nt = tt - mp * p.n_tiles;
+                const int mt = mp * p.cluster + crank;
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
                     const uint32_t fb = smem_u32(&bars->full_b[s]);
+                    if (elect_one_sync()) {
                     mbar_arrive_expect_tx(fb, tx);
-                    if (!GATHER) tma_load_2d(stage_a_hi(s), &map_a, fb, kb * BK, mt * BM);
-                    tma_load_2d(stage_b_hi(s), &map_bhi, fb, kb * BK, nt * p.BN);
-                    if (p.three_x) tma_load_2d(stage_b_lo(s), &map_blo, fb, kb * BK, nt * p.BN);
-                    if (t == (int)blockIdx.x && kb == kb0) K2Y_TRACE(2);
-                    if (t == (int)blockIdx.x && kb == kb1 - 1) K2Y_TRACE(3);
+                    if (!GATHER) {
+                        for (int bx = 0; bx < p.a_boxes; ++bx)
+                            tma_load_2d(stage_a_hi(s) + (uint32_t)bx * A_TILE_BYTES, &map_a, fb, kb * KBK + bx * BK, mt * BM);
+                    }
+                    if (p.cluster == 2) {
+                        // this CTA fetches its half of the weight tile and multicasts it into both CTAs of the pair
+                        const int half = p.BN >> 1;
+                        const uint32_t off = (uint32_t)(crank * half) * 128u;
+                        tma_load_2d_mc(stage_b_hi(s) + off, &map_bhi, fb, kb * bk_elems, nt * p.BN + crank * half, (uint16_t)3);
+                        if (p.three_x) tma_load_2d_mc(stage_b_lo(s) + off, &map_blo, fb, kb * bk_elems, nt * p.BN + crank * half, (uint16_t)3);
+                    } else {
+                        tma_load_2d(stage_b_hi(s), &map_bhi, fb, kb * bk_elems, nt * p.BN);
+                        if (p.three_x) tma_load_2d(stage_b_lo(s), &map_blo, fb, kb * bk_elems, nt * p.BN);
+                    }
+                    if (t == cluster_id && kb - kb0 < 8) K2Y_TRACE(16 + (kb - kb0) * 4);
+                    if (t == cluster_id && kb == kb0) K2Y_TRACE(2);
+                    if (t == cluster_id && kb == kb1 - 1) K2Y_TRACE(3);
+                    }
+                    __syncwarp();
                     if (++s == p.stages) {
                         s = 0;
                         ph ^= 1u;
@@ -278,12 +393,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(BM, p.BN);
+        // ================= MMA issuer (whole warp walks the loop, one elected lane issues) =================
+        {
+            const uint32_t idesc = p.bf16 ? make_idesc_bf16(BM, p.BN) : make_idesc_tf32(BM, p.BN);
             int s = 0;
             uint32_t ph = 0, acc_it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++acc_it) {
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                 mbar_wait(smem_u32(&bars->tmem_empty[a]), aph ^ 1u);
                 tc_fence_after();
@@ -291,50 +406,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int ks = t % p.k_splits;
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(smem_u32(&bars->full_b[s]), ph);
-                    if (t == (int)blockIdx.x && kb == kb0) K2Y_TRACE(4);
-                    if (use_conv) mbar_wait(smem_u32(&bars->conv[s]), ph);
-                    if (t == (int)blockIdx.x && kb == kb0) K2Y_TRACE(5);
+                    if (!(p.dbg & 8)) mbar_wait(smem_u32(&bars->full_b[s]), ph);
+                    if (t == cluster_id && kb == kb0 && lane == 0) K2Y_TRACE(4);
+                    if (use_conv && !(p.dbg & 8)) mbar_wait(smem_u32(&bars->conv[s]), ph);
+                    if (t == cluster_id && kb == kb0 && lane == 0) K2Y_TRACE(5);
                     tc_fence_after();
+                    if (elect_one_sync()) {
                     const uint64_t a_hi = make_desc_sw128(stage_a_hi(s)), b_hi = make_desc_sw128(stage_b_hi(s));
-                    const uint64_t a_lo = make_desc_sw128(stage_a_lo(s)), b_lo = make_desc_sw128(stage_b_lo(s));
+                    const uint64_t b_lo = make_desc_sw128(stage_b_lo(s));
+                    const uint32_t ta_hi = tmem_a_hi(s), ta_lo = ta_hi + 32u;
 #pragma unroll
-                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                        const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
-                        if (p.three_x) {
-                            // small terms first, then the dominant hi*hi
-                            umma_tf32(d, a_lo + adv, b_hi + adv, idesc, ((kb - kb0) | kk) != 0);
-                            umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
-                            umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1u);
+                    for (int kk = 0; kk < 4; ++kk) {  // 4 k-steps per k-block: 8 tf32 or 16 bf16 values = 32 bytes of B each
+                        if (p.dbg & 16) break;
+                        const uint64_t adv = (uint64_t)((kk * 32) >> 4);  // advance inside the 128 B swizzle row
+                        const uint32_t acol = (uint32_t)(kk * 8);          // 8 TMEM columns of A per k-step
+                        if (p.bf16) {
+                            // bf16x3: mid*hi + hi*mid + hi*hi (A planes in tensor memory, 2 bf16 per column)
+                            umma_bf16_ts(d, ta_lo + acol, b_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+                            umma_bf16_ts(d, ta_hi + acol, b_lo + adv, idesc, 1u);
+                            umma_bf16_ts(d, ta_hi + acol, b_hi + adv, idesc, 1u);
+                        } else if (p.three_x) {
+                            // 3xTF32: small terms first, then the dominant hi*hi; A comes from tensor memory
+                            umma_tf32_ts(d, ta_lo + acol, b_hi + adv, idesc, ((kb - kb0) | kk) != 0);
+                            umma_tf32_ts(d, ta_hi + acol, b_lo + adv, idesc, 1u);
+                            umma_tf32_ts(d, ta_hi + acol, b_hi + adv, idesc, 1u);
                         } else {
                             umma_tf32(d, a_hi + adv, b_hi + adv, idesc, ((kb - kb0) | kk) != 0);
                         }
                     }
-                    umma_commit(smem_u32(&bars->empty[s]));  // frees the smem slot when these MMAs retire
+                    if (t == cluster_id && kb - kb0 < 8) K2Y_TRACE(16 + (kb - kb0) * 4 + 3);
+                    if (p.cluster == 2) umma_commit_mc(smem_u32(&bars->empty[s]), (uint16_t)3);  // frees the slot in BOTH CTAs
+                    else umma_commit(smem_u32(&bars->empty[s]));  // frees the smem slot when these MMAs retire
+                    }
+                    __syncwarp();
                     if (++s == p.stages) {
                         s = 0;
                         ph ^= 1u;
                     }
                 }
-                umma_commit(smem_u32(&bars->tmem_full[a]));
-                if (t == (int)blockIdx.x) K2Y_TRACE(6);
+                if (elect_one_sync()) {
+                    umma_commit(smem_u32(&bars->tmem_full[a]));
+                    if (t == cluster_id) K2Y_TRACE(6);
+                }
+                __syncwarp();
             }
-            K2Y_TRACE(7);
+            if (lane == 0) K2Y_TRACE(7);
         }
     } else if (warp >= 2 && warp < 6) {
         // ================= A gather (implicit GEMM rows) =================
+        // Each k-block is KBK consecutive channels of one filter tap, i.e. one contiguous run per output pixel.  Thread r
+        // computes the source address of GEMM row r once per k-block; the addresses are then exchanged with warp shuffles
+        // so that 8 (tf32) or 16 (bf16) consecutive lanes copy one row's run: a cp.async warp instruction touches 4 or 2
+        // full 128-byte lines instead of 32 different ones (the L1/LSU request rate was the limiter of the 3x3 convs).
         if (GATHER) {
             const int r = threadIdx.x - 64;  // GEMM row inside the tile, 0..127
             const int Cin = p.C0 + p.C1;
+            const int wrow0 = (warp - 2) * 32;   // first tile row of this warp
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
                 const int ks = t % p.k_splits, tt = t / p.k_splits;
-                const int mt = tt / p.n_tiles;
+                const int mt = (tt / p.n_tiles) * p.cluster + crank;
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 const int m = mt * BM + r;
                 int b = -1, iy0 = 0, ix0 = 0;
-                if (m < p.M) {
+                if (m < p.M && mt < p.m_tiles) {
                     const int ox = m % p.OW;
                     const int q = m / p.OW;
                     const int oy = q % p.OH;
@@ -343,15 +479,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     ix0 = ox * p.stride - p.pad_l;
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    // a k-block = 32 consecutive channels of ONE tap of ONE source (Cin % 32 == 0, C0 % 32 == 0)
-                    const int k = kb * BK;
+                    // a k-block = KBK consecutive channels of ONE tap of ONE source (Cin % KBK == 0, C0 % KBK == 0)
+                    const int k = kb * KBK;
                     const int tap = k / Cin;
                     const int ci = k - tap * Cin;
                     const int ky = tap / p.kw, kx = tap - ky * p.kw;
                     const int iy = iy0 + ky, ix = ix0 + kx;
                     const bool ok = b >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                    const float *src = p.src0;
+                    unsigned long long pr = 0ull;  // 0 = zero-fill (padding / rows beyond M)
                     if (ok) {
+                        const float *src;
                         if (ci < p.C0) {
                             if (p.up0)
                                 src = p.src0 + ((size_t)(b * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.C0 + ci;
@@ -360,12 +497,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         } else {
                             src = p.src1 + ((size_t)(b * p.H + iy) * p.W + ix) * p.C1 + (ci - p.C0);
                         }
+                        pr = (unsigned long long)src;
                     }
                     mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-                    const uint32_t row = stage_a_hi(s) + (uint32_t)r * 128u;
-                    const uint32_t nbytes = ok ? 16u : 0u;
+                    const uint32_t stg_a = stage_a_hi(s);
+                    if (p.a_boxes == 2) {
+                        const int cjj = lane & 15;
+                        const uint32_t dcol = (uint32_t)(cjj >> 3) * A_TILE_BYTES;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) cp_async_16(row + (uint32_t)((j ^ (r & 7)) << 4), src + j * 4, nbytes);
+                        for (int i = 0; i < 16; ++i) {
+                            const int lr = 2 * i + (lane >> 4);
+                            const unsigned long long q = __shfl_sync(0xffffffffu, pr, lr);
+                            const int row = wrow0 + lr;
+                            cp_async_16(stg_a + dcol + (uint32_t)row * 128u + (uint32_t)(((cjj & 7) ^ (row & 7)) << 4),
+                                        q ? (const void *)(q + (unsigned long long)cjj * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                        }
+                    } else {
+                        const int cjj = lane & 7;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int lr = 4 * i + (lane >> 3);
+                            const unsigned long long q = __shfl_sync(0xffffffffu, pr, lr);
+                            const int row = wrow0 + lr;
+                            cp_async_16(stg_a + (uint32_t)row * 128u + (uint32_t)((cjj ^ (row & 7)) << 4),
+                                        q ? (const void *)(q + (unsigned long long)cjj * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                        }
+                    }
                     cp_async_mbar_arrive_noinc(smem_u32(&bars->full_a[s]));
                     if (++s == p.stages) {
                         s = 0;
@@ -380,33 +537,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int ct = threadIdx.x - 6 * 32;  // 0..127
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
                 const int ks = t % p.k_splits;
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(GATHER ? &bars->full_a[s] : &bars->full_b[s]), ph);
-                    if (p.three_x && !(p.dbg & 4)) {
-                        float4 *hi = reinterpret_cast<float4 *>(smem_gen + (size_t)s * stage_bytes);
-                        float4 *lo = reinterpret_cast<float4 *>(smem_gen + (size_t)s * stage_bytes + A_TILE_BYTES);
+                    if (t == cluster_id && kb - kb0 < 8 && ct == 0) K2Y_TRACE(16 + (kb - kb0) * 4 + 1);
+                    if (p.bf16) {
+                        // thread = GEMM row: 64 fp32 -> bf16 hi plane (32 columns) + bf16 mid plane (32 columns) in TMEM
+                        const int row = (warp & 3) * 32 + lane;
+                        uint32_t hi[32], lo[32];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int idx = ct + i * 128;  // element-wise: the swizzled position is irrelevant
-                            const float4 v = hi[idx];
-                            float4 h, l;
-                            h.x = to_tf32_rna(v.x);
-                            h.y = to_tf32_rna(v.y);
-                            h.z = to_tf32_rna(v.z);
-                            h.w = to_tf32_rna(v.w);
-                            l.x = to_tf32_rna(v.x - h.x);
-                            l.y = to_tf32_rna(v.y - h.y);
-                            l.z = to_tf32_rna(v.z - h.z);
-                            l.w = to_tf32_rna(v.w - h.w);
-                            hi[idx] = h;
-                            lo[idx] = l;
+                        for (int bx = 0; bx < 2; ++bx) {
+                            const uint32_t src = stage_a_hi(s) + (uint32_t)bx * A_TILE_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 v = ld_shared_v4(src + (uint32_t)((j ^ (row & 7)) << 4));
+                                const uint32_t h01 = pack_bf16x2(v.x, v.y), h23 = pack_bf16x2(v.z, v.w);
+                                const float r0 = v.x - __uint_as_float(h01 << 16), r1 = v.y - __uint_as_float(h01 & 0xffff0000u);
+                                const float r2 = v.z - __uint_as_float(h23 << 16), r3 = v.w - __uint_as_float(h23 & 0xffff0000u);
+                                hi[bx * 16 + j * 2] = h01;
+                                hi[bx * 16 + j * 2 + 1] = h23;
+                                lo[bx * 16 + j * 2] = pack_bf16x2(r0, r1);
+                                lo[bx * 16 + j * 2 + 1] = pack_bf16x2(r2, r3);
+                            }
                         }
+                        const uint32_t trow = tmem_a_hi(s) + ((uint32_t)((warp & 3) * 32) << 16);
+                        tmem_st32(trow, hi);
+                        tmem_st32(trow + 32u, lo);
+                        tmem_st_wait();
+                        tc_fence_before();
+                    } else if (p.three_x) {
+                        // thread = GEMM row: read its 128-byte (swizzled) k-slice, split, write both planes to TMEM
+                        const int row = (warp & 3) * 32 + lane;
+                        const uint32_t src = stage_a_hi(s) + (uint32_t)row * 128u;
+                        uint32_t hi[32], lo[32];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 v = ld_shared_v4(src + (uint32_t)((j ^ (row & 7)) << 4));
+                            const float h0 = to_tf32_rna(v.x), h1 = to_tf32_rna(v.y), h2 = to_tf32_rna(v.z), h3 = to_tf32_rna(v.w);
+                            hi[j * 4] = __float_as_uint(h0);
+                            hi[j * 4 + 1] = __float_as_uint(h1);
+                            hi[j * 4 + 2] = __float_as_uint(h2);
+                            hi[j * 4 + 3] = __float_as_uint(h3);
+                            lo[j * 4] = __float_as_uint(to_tf32_rna(v.x - h0));
+                            lo[j * 4 + 1] = __float_as_uint(to_tf32_rna(v.y - h1));
+                            lo[j * 4 + 2] = __float_as_uint(to_tf32_rna(v.z - h2));
+                            lo[j * 4 + 3] = __float_as_uint(to_tf32_rna(v.w - h3));
+                        }
+                        const uint32_t trow = tmem_a_hi(s) + ((uint32_t)((warp & 3) * 32) << 16);
+                        tmem_st32(trow, hi);
+                        tmem_st32(trow + 32u, lo);
+                        tmem_st_wait();
+                        tc_fence_before();
+                    } else {
+                        fence_proxy_async();  // cp.async-written A tile -> visible to the MMA (async proxy)
                     }
-                    fence_proxy_async();  // generic-proxy writes (st.shared / cp.async) -> visible to the MMA (async proxy)
                     mbar_arrive(smem_u32(&bars->conv[s]));
+                    if (t == cluster_id && kb - kb0 < 8 && ct == 0) K2Y_TRACE(16 + (kb - kb0) * 4 + 2);
                     if (++s == p.stages) {
                         s = 0;
                         ph ^= 1u;
@@ -424,19 +612,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // two 4 KB staging buffers per warp, 1024-byte aligned (SWIZZLE_128B atom)
         const uint32_t stg_base = ((smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)sizeof(Barriers) + 1023u) & ~1023u) +
                                   (uint32_t)(warp - 10) * 8192u;
+        const uint32_t ss_base = ((smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)sizeof(Barriers) + 1023u) & ~1023u) + 4u * 8192u;
         const int chunk = lane & 7, rsub = lane >> 3;
         uint32_t acc_it = 0, stg_it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++acc_it) {
             const int ks = t % p.k_splits, tt = t / p.k_splits;
-            const int mt = tt / p.n_tiles, nt = tt - mt * p.n_tiles;
+            const int mp = tt / p.n_tiles, nt = tt - mp * p.n_tiles;
+            const int mt = mp * p.cluster + crank;
+            const bool tile_ok = mt < p.m_tiles;  // odd m-tile count: the pair's second CTA only helps with the weights
             const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-            // pull this tile's scale/shift lines into L1 while the mainloop is still running
-            if (lane * 32 < p.BN && nt * p.BN + lane * 32 < p.N) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scale + nt * p.BN + lane * 32));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.shift + nt * p.BN + lane * 32));
+            // With ~227 KB of shared memory carved out there is practically no L1 left, so per-column scale/shift loads
+            // were L2 round trips on the epilogue's critical path: stage the tile's BN columns in shared memory (double
+            // buffered by tile parity) while the mainloop of this tile is still running.
+            const uint32_t ss = ss_base + (acc_it & 1u) * 2048u;
+            {
+                const int et = threadIdx.x - 10 * 32;  // 0..127
+                for (int j = et; j < ((p.BN + 31) & ~31); j += 128) {
+                    const int n = nt * p.BN + j;
+                    const bool in = j < p.BN && n < p.N;
+                    const float scv = in ? __ldg(p.scale + n) : 0.f, shv = in ? __ldg(p.shift + n) : 0.f;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss + (uint32_t)j * 4u), "f"(scv) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss + 1024u + (uint32_t)j * 4u), "f"(shv) : "memory");
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
             }
             mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
-            if (t == (int)blockIdx.x && threadIdx.x == 10 * 32) K2Y_TRACE(8);
+            if (t == cluster_id && threadIdx.x == 10 * 32) K2Y_TRACE(8);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)p.BN;
             // split-K partials of slice ks live at rows [ks * m_tiles * 128, ...) of the scratch tensor
@@ -446,6 +647,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int n0 = nt * p.BN + c0;
                 const uint32_t stg = stg_base + (stg_it & 1u) * 4096u;
                 uint32_t r[32];
+                const bool tr = p.trace && t == cluster_id && c0 == 32 && threadIdx.x == 10 * 32;
+                long long c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_4 = 0;
+                if (tr) c_0 = clock64();
                 tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
                 if (ncols == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
                 else {
@@ -453,31 +657,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int j = 16; j < 32; ++j) r[j] = 0u;
                 }
                 tmem_ld_wait();
+                if (tr) c_1 = clock64();
                 if (p.tma_store) {
-                    // scale/shift are warp-uniform broadcasts (same address in every lane)
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (n0 + j < p.N) {
-                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(p.scale + n0 + j));
-                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(p.shift + n0 + j));
-                            r[j] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j]), s4.x, h4.x), p.act_slope, p.act_clamp));
-                            r[j + 1] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j + 1]), s4.y, h4.y), p.act_slope, p.act_clamp));
-                            r[j + 2] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j + 2]), s4.z, h4.z), p.act_slope, p.act_clamp));
-                            r[j + 3] = __float_as_uint(act_bf(fmaf(__uint_as_float(r[j + 3]), s4.w, h4.w), p.act_slope, p.act_clamp));
-                        }
+                    // scale/shift come from the shared-memory copy (zero beyond N, so no bounds checks); the activation is
+                    // specialised outside the element loop: leaky = max(v, slope*v), relu = max(v,0), relu6 = min(max(v,0),6)
+#define K2Y_EPI_LOOP(ACT_EXPR)                                                                                     \
+    _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                                             \
+        const float4 s4 = ld_shared_v4(ss + (uint32_t)(c0 + j) * 4u);                                               \
+        const float4 h4 = ld_shared_v4(ss + 1024u + (uint32_t)(c0 + j) * 4u);                                       \
+        float v;                                                                                                     \
+        v = fmaf(__uint_as_float(r[j]), s4.x, h4.x);     r[j] = __float_as_uint(ACT_EXPR);                           \
+        v = fmaf(__uint_as_float(r[j + 1]), s4.y, h4.y); r[j + 1] = __float_as_uint(ACT_EXPR);                       \
+        v = fmaf(__uint_as_float(r[j + 2]), s4.z, h4.z); r[j + 2] = __float_as_uint(ACT_EXPR);                       \
+        v = fmaf(__uint_as_float(r[j + 3]), s4.w, h4.w); r[j + 3] = __float_as_uint(ACT_EXPR);                       \
+    }
+                    if (p.act == ACT_LEAKY) {
+                        const float slope = p.act_slope;
+                        K2Y_EPI_LOOP(fmaxf(v, v * slope))
+                    } else if (p.act == ACT_RELU) {
+                        K2Y_EPI_LOOP(fmaxf(v, 0.f))
+                    } else if (p.act == ACT_RELU6) {
+                        K2Y_EPI_LOOP(fminf(fmaxf(v, 0.f), 6.f))
+                    } else {
+                        K2Y_EPI_LOOP(v)
                     }
+#undef K2Y_EPI_LOOP
+                    if (tr) c_2 = clock64();
                     // the staging buffer used two chunks ago must have been read by its TMA store
                     if (lane == 0) tma_store_wait_read1();
                     __syncwarp();
+                    if (tr) c_3 = clock64();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[j * 4], r[j * 4 + 1],
                                      r[j * 4 + 2], r[j * 4 + 3]);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && !(p.dbg & 1)) {
+                    if (tr) c_4 = clock64();
+                    if (lane == 0 && tile_ok && !(p.dbg & 1)) {
                         tma_store_2d(&map_out, stg, n0, m_base);  // rows >= M and columns >= N are clipped by the TMA
                         tma_store_commit();
+                    }
+                    if (tr) {
+                        long long *o = p.trace + (size_t)blockIdx.x * 64 + 48;
+                        o[0] = c_1 - c_0;
+                        o[1] = c_2 - c_1;
+                        o[2] = c_3 - c_2;
+                        o[3] = c_4 - c_3;
+                        o[4] = clock64() - c_4;
                     }
                 } else {
 #pragma unroll
@@ -493,8 +720,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (n + j < p.N) {
-                                sc[j] = __ldg(p.scale + n + j);
-                                sh[j] = __ldg(p.shift + n + j);
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc[j]) : "r"(ss + (uint32_t)(c0 + chunk * 4 + j) * 4u));
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sh[j]) : "r"(ss + 1024u + (uint32_t)(c0 + chunk * 4 + j) * 4u));
                             }
                     }
 #pragma unroll
@@ -502,7 +729,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int row = it * 4 + rsub;
                         const int m = m_base + row;
                         const float4 v = ld_shared_v4(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
-                        if (col_ok && m < p.M && !(p.dbg & 1)) {
+                        if (col_ok && tile_ok && m < p.M && !(p.dbg & 1)) {
                             float o[4];
                             o[0] = act_bf(fmaf(v.x, sc[0], sh[0]), p.act_slope, p.act_clamp);
                             o[1] = act_bf(fmaf(v.y, sc[1], sh[1]), p.act_slope, p.act_clamp);
@@ -527,14 +754,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->tmem_empty[a]));
-            if (t == (int)blockIdx.x && threadIdx.x == 10 * 32) K2Y_TRACE(9);
+            if (t == cluster_id && threadIdx.x == 10 * 32) K2Y_TRACE(9);
         }
         if (p.tma_store && lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
         if (threadIdx.x == 10 * 32) K2Y_TRACE(10);
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster == 2) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
+    else __syncthreads();
     if (threadIdx.x == 0) K2Y_TRACE(11);
     if (warp == 1) {
         tc_fence_after();
@@ -591,21 +819,35 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows][cols] tensor, box = [box_rows][32 cols], 128B swizzle, OOB -> 0.
-bool make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t pitch_elems = 0) {
+// 2-D row-major [rows][cols] tensor (fp32 or bf16), box = [box_rows][128 bytes of columns], 128B swizzle, OOB -> 0.
+bool make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t pitch_elems = 0,
+                 bool bf16 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
+    const size_t esz = bf16 ? 2 : 4;
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {(pitch_elems ? pitch_elems : cols) * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint64_t strides[1] = {(pitch_elems ? pitch_elems : cols) * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
 float __int_as_float_host(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+uint16_t bf16_rne_host(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+float bf16_to_float_host(uint16_t b) {
+    const uint32_t u = (uint32_t)b << 16;
     float f;
     memcpy(&f, &u, 4);
     return f;
@@ -637,23 +879,50 @@ constexpr int ID_LEN = 4096;
 // in profiles/): a work item costs  kb * max(MMA time, pipeline latency / depth) + epilogue + fixed,  the layer costs
 // ceil(items / SMs) item times (+ the reduction pass when K is split).  A is re-read once per n-tile, so ties go to
 // the wider tile; BN is a multiple of 32 when N is tiled (TMA-store boxes are 32 columns wide).
-void pick_tile(int M, int N, int nkb, bool three_x, int *bn_out, int *splits_out) {
+// CTA pairs (cluster of 2 on adjacent m-tiles) fetch each weight tile once and multicast it: halves the L2 -> SM
+// weight traffic that bounds the K-deep layers.  Not worth the cluster sync for single-tile or 1-2 k-block layers.
+int pick_cluster(int M, int nkb) {
+    const char *force = getenv("K2Y_TC_CLUSTER");
+    if (force) return atoi(force) == 2 ? 2 : 1;
+    return ((M + BM - 1) / BM >= 2 && nkb >= 4) ? 2 : 1;
+}
+
+void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int cluster, int *bn_out, int *splits_out) {
     const int n16 = (N + 15) / 16 * 16;
     const int m_tiles = (M + BM - 1) / BM;
     const int sms = g_num_sms > 0 ? g_num_sms : 148;
     const char *force = getenv("K2Y_TC_SPLITK");
     int best = 16, best_s = 1;
     double best_cost = 1e30;
+    const char *force_bn = getenv("K2Y_TC_BN");
     for (int bn = 16; bn <= 256; bn += 16) {
         if (bn > n16) break;
-        const size_t stage = (size_t)A_TILE_BYTES * (three_x ? 2 : 1) + (size_t)bn * 128 * (three_x ? 2 : 1);
-        const int stages = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage);
-        if (stages < 3 && bn > 16) continue;
+        if (force_bn && bn != atoi(force_bn)) continue;
+        const size_t a_bytes = (size_t)A_TILE_BYTES * (bf16 ? 2 : 1);
+        const size_t stage = a_bytes + (size_t)bn * 128 * (three_x ? 2 : 1);
+        int stages = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage);
+        if (three_x) stages = stages < (512 - 2 * bn) / 64 ? stages : (512 - 2 * bn) / 64;  // A planes live in TMEM: 64 columns / stage
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+        if (stages < 3 && bn > 16 && !force_bn) continue;
+        if (stages < 2) continue;
         const int n_tiles = (n16 + bn - 1) / bn;
         if (n_tiles > 1 && (bn % 32) != 0) continue;
-        const double mma = (three_x ? 3.0 : 1.0) * 4.0 * (bn / 2.0);       // 4 k-steps of 128 x bn x 8 per pass
-        const double lat = 4400.0 / (stages < 8 ? stages : 8);               // load->convert->mma->free round trip / depth
-        const double kbt = mma > lat ? mma : lat;
+        // per k-block (32 k for tf32, 64 k for bf16): tensor time (measured: a tf32 MMA of 128 x bn x 8 takes ~bn cycles, a bf16
+        // MMA of 128 x bn x 16 ~bn/2), shared-memory traffic (TMA fill + converter read + MMA operand reads) at 128 B/clk,
+        // and the load->convert->mma->free round trip divided by the pipeline depth
+        // calibrated on the per-k-block timelines (profiles/): issue-bound MMA floor, converter pass, gather issue, and the
+        // load -> convert -> mma -> free round trip (~3000 cycles, ~5000 when A is gathered) divided by the pipeline depth
+        const double passes = three_x ? 3.0 : 1.0;
+        double mma = passes * 4.0 * (bf16 ? bn / 2.0 : (double)bn);
+        if (mma < passes * 4.0 * 30.0) mma = passes * 4.0 * 30.0;
+        const double conv = three_x ? (bf16 ? 700.0 : 450.0) : 0.0;
+        const double smem_bytes = (double)a_bytes + bn * 128.0 * (three_x ? 2 : 1) + (three_x ? (double)a_bytes : 4.0 * 4096.0) +
+                                  passes * 4.0 * bn * 32.0;
+        const double smem_t = smem_bytes / 128.0;
+        const double lat = (gather ? 5000.0 : 3000.0) / stages;
+        double kbt = mma > lat ? mma : lat;
+        if (conv > kbt) kbt = conv;
+        if (smem_t > kbt) kbt = smem_t;
         const double waste = (double)(n_tiles * bn) / n16;                   // zero-padded columns still cost MMA time
         for (int sp = 1; sp <= 8; ++sp) {
             if (force && sp != atoi(force) && !(atoi(force) < 1 && sp == 1)) continue;
@@ -662,9 +931,10 @@ void pick_tile(int M, int N, int nkb, bool three_x, int *bn_out, int *splits_out
                 if ((size_t)sp * m_tiles * BM * N * sizeof(float) > g_scratch_bytes) continue;
             }
             const int kb = (nkb + sp - 1) / sp;
-            const long items = (long)m_tiles * n_tiles * sp;
-            const double item = kb * kbt + bn * 12.0 + 2500.0;
-            double cost = (double)((items + sms - 1) / sms) * item * (0.9 + 0.1 * waste) + n_tiles * 40.0;
+            const long items = (long)((m_tiles + cluster - 1) / cluster) * n_tiles * sp;  // per cluster
+            const int units = sms / cluster;
+            const double item = kb * kbt + bn * 35.0 + 2500.0;  // epilogue ~1100 cycles per 32 columns
+            double cost = (double)((items + units - 1) / units) * item * (0.9 + 0.1 * waste) + n_tiles * 40.0;
             if (sp > 1) cost += 7000.0 + (double)sp * M * N * 4.0 / 1500.0;  // reduce pass: launch + partial traffic
             if (cost < best_cost) {
                 best_cost = cost;
@@ -721,13 +991,38 @@ int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N) {
     K2Y_CUDA_CHECK(cudaMalloc(&w.d_lo, lo.size() * sizeof(float)));
     K2Y_CUDA_CHECK(cudaMemcpy(w.d_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
     K2Y_CUDA_CHECK(cudaMemcpy(w.d_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // bf16x3 planes
+    w.Kpad64 = (K + 63) / 64 * 64;
+    std::vector<uint16_t> bh((size_t)w.Npad * w.Kpad64, 0), bm((size_t)w.Npad * w.Kpad64, 0);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) {
+            const float v = kernel_kn[(size_t)k * N + n];
+            const uint16_t h = bf16_rne_host(v);
+            bh[(size_t)n * w.Kpad64 + k] = h;
+            bm[(size_t)n * w.Kpad64 + k] = bf16_rne_host(v - bf16_to_float_host(h));
+        }
+    K2Y_CUDA_CHECK(cudaMalloc(&w.d_bh, bh.size() * sizeof(uint16_t)));
+    K2Y_CUDA_CHECK(cudaMalloc(&w.d_bm, bm.size() * sizeof(uint16_t)));
+    K2Y_CUDA_CHECK(cudaMemcpy(w.d_bh, bh.data(), bh.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    K2Y_CUDA_CHECK(cudaMemcpy(w.d_bm, bm.data(), bm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     return K2Y_OK;
 }
 
 void tc_free(TcWeights &w) {
     cudaFree(w.d_hi);
     cudaFree(w.d_lo);
+    cudaFree(w.d_bh);
+    cudaFree(w.d_bm);
     w = TcWeights();
+}
+
+// bf16x3 needs whole 64-channel k-blocks per tap in the gather path; layers that do not fit run as 3xTF32
+static bool is_plain_1x1(const ConvArgs &a);
+static int effective_mode(const ConvArgs &a, int math_mode) {
+    if (math_mode != K2Y_MATH_TC_BF16X3) return math_mode;
+    if (is_plain_1x1(a)) return math_mode;
+    const int Cin = a.C0 + a.C1;
+    return ((Cin % 64) == 0 && (a.C0 % 64) == 0) ? math_mode : K2Y_MATH_TC_3XTF32;
 }
 
 static bool is_plain_1x1(const ConvArgs &a) {
@@ -771,22 +1066,27 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.M = a.B * a.OH * a.OW;
     p.N = a.N;
     p.K = w.K;
-    p.three_x = (math_mode == K2Y_MATH_TC_3XTF32) ? 1 : 0;
-    p.nkb = w.Kpad / BK;
-    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, &p.BN, &p.k_splits);
+    math_mode = effective_mode(a, math_mode);
+    p.bf16 = (math_mode == K2Y_MATH_TC_BF16X3) ? 1 : 0;
+    p.three_x = (math_mode == K2Y_MATH_TC_TF32) ? 0 : 1;
+    p.a_boxes = p.bf16 ? 2 : 1;
+    p.nkb = p.bf16 ? w.Kpad64 / 64 : w.Kpad / BK;
+    p.cluster = pick_cluster(p.M, p.nkb);
+    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a), p.cluster, &p.BN, &p.k_splits);
     p.n_tiles = (w.Npad + p.BN - 1) / p.BN;
     p.m_tiles = (p.M + BM - 1) / BM;
     p.kb_per_split = (p.nkb + p.k_splits - 1) / p.k_splits;
     p.k_splits = (p.nkb + p.kb_per_split - 1) / p.kb_per_split;  // no empty slices
-    uint32_t cols = 32;
-    while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
-    p.tmem_cols = cols;
-    const size_t stage_bytes = (size_t)A_TILE_BYTES * (p.three_x ? 2 : 1) + (size_t)p.BN * 128 * (p.three_x ? 2 : 1);
+    const size_t stage_bytes = (size_t)A_TILE_BYTES * p.a_boxes + (size_t)p.BN * 128 * (p.three_x ? 2 : 1);
     const size_t fixed = FIXED_SMEM;
     int stages = (int)((g_max_smem - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (p.three_x && stages > (512 - 2 * p.BN) / 64) stages = (512 - 2 * p.BN) / 64;  // TMEM: 2 accumulators + 64 columns of A per stage
     if (stages < 2) return cudaErrorInvalidConfiguration;
     p.stages = stages;
+    uint32_t cols = 32;
+    while (cols < 2u * (uint32_t)p.BN + (p.three_x ? 64u * (uint32_t)stages : 0u)) cols <<= 1;
+    p.tmem_cols = cols;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
 
     const bool gather = !is_plain_1x1(a);
@@ -803,6 +1103,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         p.residual = nullptr;
         p.scale = g_ones;
         p.shift = g_zeros;
+        p.act = ACT_NONE;
         p.act_slope = 1.f;
         p.act_clamp = __int_as_float_host(0x7f800000);
         if (!make_map_2d(&map_out, g_scratch, (uint64_t)p.k_splits * mpad, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
@@ -810,39 +1111,68 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         return cudaErrorInvalidValue;
     }
     if (!gather && !make_map_2d(&map_a, a.src0, (uint64_t)p.M, (uint64_t)(a.C0 + a.C1), BM)) return cudaErrorInvalidValue;
-    if (!make_map_2d(&map_bhi, w.d_hi, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
-    if (!make_map_2d(&map_blo, w.d_lo, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)p.BN)) return cudaErrorInvalidValue;
+    if (p.bf16) {
+        if (!make_map_2d(&map_bhi, w.d_bh, (uint64_t)w.Npad, (uint64_t)w.Kpad64, (uint32_t)(p.BN / p.cluster), 0, true)) return cudaErrorInvalidValue;
+        if (!make_map_2d(&map_blo, w.d_bm, (uint64_t)w.Npad, (uint64_t)w.Kpad64, (uint32_t)(p.BN / p.cluster), 0, true)) return cudaErrorInvalidValue;
+    } else {
+        if (!make_map_2d(&map_bhi, w.d_hi, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)(p.BN / p.cluster))) return cudaErrorInvalidValue;
+        if (!make_map_2d(&map_blo, w.d_lo, (uint64_t)w.Npad, (uint64_t)w.Kpad, (uint32_t)(p.BN / p.cluster))) return cudaErrorInvalidValue;
+    }
 
-    const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int tiles = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_tiles * p.k_splits;  // work items per cluster
+    const int max_clusters = g_num_sms / p.cluster;
+    const int grid = (tiles < max_clusters ? tiles : max_clusters) * p.cluster;
     p.trace = nullptr;
     p.dbg = getenv("K2Y_TC_DBG") ? atoi(getenv("K2Y_TC_DBG")) : 0;
     const char *tr = getenv("K2Y_TC_TRACE");
     long long *d_trace = nullptr;
     if (tr && tr[0] == '1') {
-        cudaMalloc(&d_trace, (size_t)grid * 16 * sizeof(long long));
-        cudaMemset(d_trace, 0, (size_t)grid * 16 * sizeof(long long));
+        cudaMalloc(&d_trace, (size_t)grid * 64 * sizeof(long long));
+        cudaMemset(d_trace, 0, (size_t)grid * 64 * sizeof(long long));
         p.trace = d_trace;
-        fprintf(stderr, "[tc-trace] M=%d N=%d K=%d BN=%d tiles=%d (m %d x n %d x k %d) nkb=%d stages=%d grid=%d gather=%d 3x=%d smem=%zu\n", p.M,
-                p.N, p.K, p.BN, tiles, p.m_tiles, p.n_tiles, p.k_splits, p.nkb, p.stages, grid, (int)gather, p.three_x, smem);
+        fprintf(stderr, "[tc-trace] M=%d N=%d K=%d BN=%d items=%d (m %d x n %d x k %d) cluster=%d nkb=%d stages=%d grid=%d gather=%d 3x=%d smem=%zu\n",
+                p.M, p.N, p.K, p.BN, tiles, p.m_tiles, p.n_tiles, p.k_splits, p.cluster, p.nkb, p.stages, grid, (int)gather, p.three_x + 2 * p.bf16, smem);
     }
-    if (gather)
-        conv_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, p);
-    else
-        conv_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_out, p);
+    {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, map_a, map_bhi, map_blo, map_out, p)
+                                : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, map_a, map_bhi, map_blo, map_out, p);
+        if (le != cudaSuccess) return le;
+    }
     if (d_trace) {
         cudaStreamSynchronize(st);
-        std::vector<long long> h((size_t)grid * 16);
+        std::vector<long long> h((size_t)grid * 64);
         cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(d_trace);
         long long t0 = h[0];
         for (int b = 0; b < grid; ++b)
-            if (h[(size_t)b * 16] && h[(size_t)b * 16] < t0) t0 = h[(size_t)b * 16];
+            if (h[(size_t)b * 64] && h[(size_t)b * 64] < t0) t0 = h[(size_t)b * 64];
         static const char *names[13] = {"start", "setup_done", "tma_first", "tma_tile0_last", "mma_full_b0", "mma_conv0", "mma_tile0_commit",
                                         "mma_all_issued", "epi_tile0_ready", "epi_tile0_done", "epi_all_done", "all_synced", "dealloc"};
         for (int b : {0, grid / 2, grid - 1}) {
             fprintf(stderr, "[tc-trace] cta %d:", b);
-            for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%.2fus", names[i], h[(size_t)b * 16 + i] ? (h[(size_t)b * 16 + i] - t0) * 1e-3 : -1.0);
+            for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%.2fus", names[i], h[(size_t)b * 64 + i] ? (h[(size_t)b * 64 + i] - t0) * 1e-3 : -1.0);
+            fprintf(stderr, "\n");
+        }
+        // per-k-block pipeline of CTA 0's first tile: tma issue / landed (converter sees it) / converted / mma issued / slot free again
+        fprintf(stderr, "[tc-trace] epilogue chunk cycles: tmem_ld+wait=%lld math=%lld wait_read=%lld sts+fence=%lld tma_issue=%lld\n", h[48],
+                h[49], h[50], h[51], h[52]);
+        fprintf(stderr, "[tc-trace] kb: tma_issue landed converted mma_issued\n");
+        for (int kb = 0; kb < 8; ++kb) {
+            fprintf(stderr, "[tc-trace]  %d:", kb);
+            for (int e = 0; e < 4; ++e) fprintf(stderr, " %.2f", h[16 + kb * 4 + e] ? (h[16 + kb * 4 + e] - t0) * 1e-3 : -1.0);
             fprintf(stderr, "\n");
         }
     }
@@ -861,7 +1191,10 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
 
 int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode) {
     int bn = 0, splits = 1;
-    pick_tile(a.B * a.OH * a.OW, a.N, w.Kpad / BK, math_mode == K2Y_MATH_TC_3XTF32, &bn, &splits);
+    const int mode = effective_mode(a, math_mode);
+    const bool bf = mode == K2Y_MATH_TC_BF16X3;
+    const int M = a.B * a.OH * a.OW, nkb = bf ? w.Kpad64 / 64 : w.Kpad / BK;
+    pick_tile(M, a.N, nkb, mode != K2Y_MATH_TC_TF32, bf, !is_plain_1x1(a), pick_cluster(M, nkb), &bn, &splits);
     return splits > 1 ? 2 : 1;
 }
 

@@ -9,7 +9,9 @@ namespace k2y {
 struct TcWeights {
     float *d_hi = nullptr;
     float *d_lo = nullptr;
-    int K = 0, N = 0, Kpad = 0, Npad = 0;
+    unsigned short *d_bh = nullptr;  // bf16x3: bf16(w) and bf16(w - hi) planes, K-major [Npad][Kpad64]
+    unsigned short *d_bm = nullptr;
+    int K = 0, N = 0, Kpad = 0, Kpad64 = 0, Npad = 0;
 };
 
 int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N);  // kernel_kn: [K][N] row-major (Keras HWIO flattened)

@@ -72,7 +72,7 @@ struct k2y_net {
     std::vector<int> outputs;  // tensor ids
     std::map<std::string, int> auto_count;
     bool finalized = false, bound = false, keep_all = false, use_graph = true;
-    int math = K2Y_MATH_TC_3XTF32;  // default: tensor cores with fp32-class accuracy
+    int math = K2Y_MATH_TC_BF16X3;  // default: bf16 tensor cores on (hi, mid) split operands
     size_t arena_floats = 0;
     float *arena = nullptr;
     const float *x_dev = nullptr;
@@ -674,7 +674,8 @@ extern "C" int k2y_net_finalize(k2y_net *net) {
 
 extern "C" int k2y_net_set_math(k2y_net *net, int math_mode) {
     if (check_net(net, "k2y_net_set_math")) return K2Y_ERR_INVALID;
-    if (math_mode != K2Y_MATH_FP32_SIMT && math_mode != K2Y_MATH_TC_3XTF32 && math_mode != K2Y_MATH_TC_TF32) {
+    if (math_mode != K2Y_MATH_FP32_SIMT && math_mode != K2Y_MATH_TC_3XTF32 && math_mode != K2Y_MATH_TC_TF32 &&
+        math_mode != K2Y_MATH_TC_BF16X3) {
         set_error("k2y_net_set_math: unknown mode %d", math_mode);
         return K2Y_ERR_INVALID;
     }

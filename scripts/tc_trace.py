@@ -6,7 +6,8 @@ import numpy as np, torch
 from k210_yolo_framework_b200 import _lib
 from k210_yolo_framework_b200._lib import check, lib
 
-def run(B, H, W, C0, C1, up0, Cout, k, math=1, reps=2):
+def run(B, H, W, C0, C1, up0, Cout, k, math=None, reps=2):
+    math = int(os.environ.get("K2Y_TRACE_MATH", "1")) if math is None else math
     rng = np.random.default_rng(0)
     x0 = torch.randn((B, H, W, C0), device="cuda")
     hh, ww = (H * 2, W * 2) if up0 else (H, W)
@@ -21,6 +22,7 @@ def run(B, H, W, C0, C1, up0, Cout, k, math=1, reps=2):
                              sc.ctypes.data, sh.ctypes.data, B, hh, ww, C0, C1, int(up0), Cout, k, 1, 0, 1, 0.1, math,
                              ctypes.c_void_p(st.cuda_stream)))
 
+MATH = int(os.environ.get("K2Y_TRACE_MATH", "1"))
 which = sys.argv[1:] or ["h1o", "pw1", "pw3", "pw7", "h13"]
 if "h1o" in which: run(32, 7, 10, 192, 0, 0, 75, 1)      # head1_out
 if "pw1" in which: run(32, 112, 160, 24, 0, 0, 48, 1)    # pw1

@@ -9,7 +9,9 @@ from k210_yolo_framework_b200 import _lib, yolonet
 from k210_yolo_framework_b200.weights import random_weights
 from oracle import keras_ref
 
-MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_TC_3XTF32]
+MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_TC_3XTF32, _lib.MATH_TC_BF16X3]
+# per-layer error budget relative to the layer's max |activation| (fp64 oracle): fp32-class modes vs the ~16-bit-mantissa bf16x3
+LAYER_TOL = {_lib.MATH_FP32_SIMT: 2e-4, _lib.MATH_TC_3XTF32: 2e-4, _lib.MATH_TC_BF16X3: 6e-4}
 
 
 def _maxerr(a, b):
@@ -46,10 +48,11 @@ def test_mobilev1_real_weights_layerwise(golden_weights, dog_u8, dog_heads, math
         scale = max(1.0, float(np.abs(ref).max()))
         err = _maxerr(got, ref) / scale
         worst[name] = err
-        assert err < 2e-4, f"{name}: rel-to-max error {err:.3e} ({_lib.MATH_NAMES[math]})"
+        assert err < LAYER_TOL[math], f"{name}: rel-to-max error {err:.3e} ({_lib.MATH_NAMES[math]})"
     # heads: absolute logit error well inside the 1e-3 score/box budget
-    assert _maxerr(heads[0], dog_heads["l0_f64"]) < 5e-3
-    assert _maxerr(heads[1], dog_heads["l1_f64"]) < 5e-3
+    e0, e1 = _maxerr(heads[0], dog_heads["l0_f64"]), _maxerr(heads[1], dog_heads["l1_f64"])
+    print(f"[{_lib.MATH_NAMES[math]}] head logit max abs error vs fp64 oracle: {e0:.2e} {e1:.2e}; worst layer {max(worst.values()):.2e}")
+    assert e0 < 5e-3 and e1 < 5e-3
     # wrapper view
     hw = w.predict(x)
     assert hw[0].shape == (1, 7, 10, 3, 25) and hw[1].shape == (1, 14, 20, 3, 25)
@@ -74,7 +77,7 @@ def test_random_weights_all_models(model_def, alpha, classes, hw, batch, math):
     for g, r in zip(got, ref):
         assert g.shape == r.shape
         scale = max(1.0, float(np.abs(r).max()))
-        assert _maxerr(g, r) / scale < 2e-4, f"{model_def} {_lib.MATH_NAMES[math]}: {_maxerr(g, r):.3e} (max |ref| {scale:.2f})"
+        assert _maxerr(g, r) / scale < LAYER_TOL[math], f"{model_def} {_lib.MATH_NAMES[math]}: {_maxerr(g, r):.3e} (max |ref| {scale:.2f})"
 
 
 def test_device_api_graph_replay_and_batching():
