@@ -85,6 +85,11 @@ int k2y_net_workspace_bytes(const k2y_net *net, size_t *bytes);
  * x [max_batch,H,W,3] f32 NHWC and one buffer per head [max_batch,h,w,c] f32 NHWC. */
 int k2y_net_bind(k2y_net *net, void *workspace, size_t workspace_bytes, const float *x_dev,
                  float *const *heads_dev, int n_heads);
+/* Optional uint8 front end (the reference's `img / np.max(img)`, tools/utils.py:405, done on the GPU): x_u8_dev is
+ * [max_batch,H,W,3] uint8 letterboxed RGB, img_max_dev a scratch int32[max_batch].  Each run first reduces the per-image
+ * maximum, and the first convolution reads x = u8 / max through a 256-entry table (bit-identical to the float32 input the
+ * reference feeds).  Pass NULL, NULL to return to the float32 input bound with k2y_net_bind. */
+int k2y_net_bind_u8(k2y_net *net, const unsigned char *x_u8_dev, int32_t *img_max_dev);
 /* predict on bound device buffers (keras_inference.py:88), asynchronous on `stream`. */
 int k2y_net_run(k2y_net *net, int batch, void *stream);
 /* predict with HOST buffers: H2D of x, run, D2H of every head, stream-synchronised on return.

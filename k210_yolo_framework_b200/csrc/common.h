@@ -40,6 +40,9 @@ struct ConvArgs {
     int kh, kw, stride, pad_t, pad_l;
     int act;
     float alpha;
+    // first layer only: uint8 pixels + per-image maximum; the kernel feeds x = u8 / max  (tools/utils.py:405 `img / np.max(img)`)
+    const unsigned char *src_u8 = nullptr;
+    const int *img_max = nullptr;
 };
 
 struct DwArgs {
@@ -63,6 +66,7 @@ struct PoolArgs {
 cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st);
 cudaError_t launch_dwconv(const DwArgs &a, cudaStream_t st);
 cudaError_t launch_maxpool(const PoolArgs &a, cudaStream_t st);
+cudaError_t launch_image_max_u8(const unsigned char *x, int batch, size_t bytes_per_image, int *max_out, cudaStream_t st);
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
     if (act == ACT_LEAKY) return v >= 0.f ? v : v * alpha;

@@ -267,20 +267,25 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const DwArgs a) {
 
 // First convolution of every network: 3x3, Cin = 3, Cout in {16, 24, 32}.  One thread = one output pixel, all
 // output channels; the 27 x COUT weights sit in shared memory and are read as warp-wide broadcasts.
-template <int COUT>
+template <int COUT, bool U8>
 __global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a) {
     __shared__ __align__(16) float ws[27 * COUT];
     __shared__ __align__(16) float sc[COUT], sh[COUT];
+    __shared__ float lut[U8 ? 256 : 1];  // u8 -> u8 / max(image) with the IEEE division the reference's float32 cast implies
     for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) ws[i] = a.w[i];
     if (threadIdx.x < COUT) {
         sc[threadIdx.x] = a.scale[threadIdx.x];
         sh[threadIdx.x] = a.shift[threadIdx.x];
     }
+    const int row = blockIdx.y;
+    const int oy = row % a.OH, b = row / a.OH;
+    if (U8) {
+        const float mx = (float)a.img_max[b];
+        for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = __fdiv_rn((float)v, mx);
+    }
     __syncthreads();
     const int ox = blockIdx.x * blockDim.x + threadIdx.x;
     if (ox >= a.OW) return;
-    const int row = blockIdx.y;
-    const int oy = row % a.OH, b = row / a.OH;
     const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
     float in[27];
 #pragma unroll
@@ -290,9 +295,15 @@ __global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a) {
         for (int kx = 0; kx < 3; ++kx) {
             const int ix = ix0 + kx;
             const bool ok = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-            const float *p = a.src0 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
+            if (U8) {
+                const unsigned char *p8 = a.src_u8 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) in[(ky * 3 + kx) * 3 + ci] = ok ? __ldg(p + ci) : 0.f;
+                for (int ci = 0; ci < 3; ++ci) in[(ky * 3 + kx) * 3 + ci] = ok ? lut[__ldg(p8 + ci)] : 0.f;
+            } else {
+                const float *p = a.src0 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) in[(ky * 3 + kx) * 3 + ci] = ok ? __ldg(p + ci) : 0.f;
+            }
         }
     }
     float acc[COUT];
@@ -319,6 +330,24 @@ __global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a) {
         o.w = apply_act(fmaf(acc[n + 3], sc[n + 3], sh[n + 3]), a.act, a.alpha);
         *reinterpret_cast<float4 *>(outp + n) = o;
     }
+}
+
+// Per-image maximum of a uint8 batch (np.max(img) of tools/utils.py:405): grid = (chunks, B), atomicMax into int[B].
+__global__ void __launch_bounds__(256) image_max_u8_kernel(const unsigned char *__restrict__ x, size_t bytes_per_image,
+                                                           int *__restrict__ max_out) {
+    const unsigned char *img = x + (size_t)blockIdx.y * bytes_per_image;
+    const size_t n16 = bytes_per_image / 16;
+    unsigned m = 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img) + i);
+        m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+    }
+    for (size_t i = n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes_per_image; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, (unsigned)img[i]);
+    unsigned r = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = max(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if ((threadIdx.x & 31) == 0 && r > 0) atomicMax(max_out + blockIdx.y, (int)r);
 }
 
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const PoolArgs a) {
@@ -358,9 +387,15 @@ cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
     const int M = a.B * a.OH * a.OW;
     if (a.kh == 3 && a.kw == 3 && a.C0 == 3 && a.C1 == 0 && !a.up0 && !a.residual && (a.N == 16 || a.N == 24 || a.N == 32)) {
         dim3 grid((a.OW + 127) / 128, a.B * a.OH);
-        if (a.N == 16) first_conv3x3_kernel<16><<<grid, 128, 0, st>>>(a);
-        else if (a.N == 24) first_conv3x3_kernel<24><<<grid, 128, 0, st>>>(a);
-        else first_conv3x3_kernel<32><<<grid, 128, 0, st>>>(a);
+        if (a.src_u8) {
+            if (a.N == 16) first_conv3x3_kernel<16, true><<<grid, 128, 0, st>>>(a);
+            else if (a.N == 24) first_conv3x3_kernel<24, true><<<grid, 128, 0, st>>>(a);
+            else first_conv3x3_kernel<32, true><<<grid, 128, 0, st>>>(a);
+        } else {
+            if (a.N == 16) first_conv3x3_kernel<16, false><<<grid, 128, 0, st>>>(a);
+            else if (a.N == 24) first_conv3x3_kernel<24, false><<<grid, 128, 0, st>>>(a);
+            else first_conv3x3_kernel<32, false><<<grid, 128, 0, st>>>(a);
+        }
         return cudaGetLastError();
     }
     const bool vec = (a.C0 % 4 == 0) && (a.C1 % 4 == 0);
@@ -391,6 +426,14 @@ cudaError_t launch_dwconv(const DwArgs &a, cudaStream_t st) {
         dwconv3x3_kernel<1, TX><<<grid, 128, 0, st>>>(a);
     else
         dwconv3x3_kernel<2, TX><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_image_max_u8(const unsigned char *x, int batch, size_t bytes_per_image, int *max_out, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(max_out, 0, (size_t)batch * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    dim3 grid(64, batch);
+    image_max_u8_kernel<<<grid, 256, 0, st>>>(x, bytes_per_image, max_out);
     return cudaGetLastError();
 }
 

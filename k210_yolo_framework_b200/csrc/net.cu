@@ -76,6 +76,8 @@ struct k2y_net {
     size_t arena_floats = 0;
     float *arena = nullptr;
     const float *x_dev = nullptr;
+    const unsigned char *x_u8 = nullptr;  // optional uint8 input (k2y_net_bind_u8)
+    int *img_max = nullptr;
     std::vector<float *> heads_dev;
     std::map<int, cudaGraphExec_t> graphs;
     int last_batch = 0;
@@ -387,6 +389,14 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
     int li = 0;
     n->launches = 0;
     if (ev) cudaEventRecord(ev[0], st);
+    if (n->x_u8) {  // np.max(img) per image, consumed by the first conv's u8 -> f32 look-up table
+        cudaError_t e0 = launch_image_max_u8(n->x_u8, batch, (size_t)n->in_h * n->in_w * 3, n->img_max, st);
+        if (e0 != cudaSuccess) {
+            set_error("image max: launch failed: %s", cudaGetErrorString(e0));
+            return K2Y_ERR_CUDA;
+        }
+        n->launches += 1;
+    }
     for (Layer &L : n->layers) {
         const Tensor &s0 = n->tensors[L.src0];
         const Tensor &d = n->tensors[L.dst];
@@ -416,6 +426,14 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
             a.pad_l = L.pad_l;
             a.act = L.act;
             a.alpha = L.alpha;
+            if (n->x_u8 && n->tensors[L.src0].is_input) {
+                if (!(L.kh == 3 && s0.c == 3 && L.src1 < 0 && (L.cout == 16 || L.cout == 24 || L.cout == 32))) {
+                    set_error("uint8 input is only supported in front of a 3x3, Cin=3 first convolution");
+                    return K2Y_ERR_STATE;
+                }
+                a.src_u8 = n->x_u8;
+                a.img_max = n->img_max;
+            }
             if (n->math != K2Y_MATH_FP32_SIMT && tc_supported(a, L.tc)) {
                 e = launch_conv_tc(a, L.tc, n->math, st);
                 n->launches += tc_launch_count(a, L.tc, n->math);
@@ -750,6 +768,18 @@ extern "C" int k2y_net_bind(k2y_net *net, void *workspace, size_t workspace_byte
             return K2Y_ERR_INVALID;
         }
     net->bound = true;
+    drop_graphs(net);
+    return K2Y_OK;
+}
+
+extern "C" int k2y_net_bind_u8(k2y_net *net, const unsigned char *x_u8_dev, int32_t *img_max_dev) {
+    if (check_net(net, "k2y_net_bind_u8")) return K2Y_ERR_INVALID;
+    if ((x_u8_dev == nullptr) != (img_max_dev == nullptr) || (((uintptr_t)x_u8_dev) & 15) != 0) {
+        set_error("k2y_net_bind_u8: pass both pointers (16-byte aligned input) or both NULL");
+        return K2Y_ERR_INVALID;
+    }
+    net->x_u8 = x_u8_dev;
+    net->img_max = img_max_dev;
     drop_graphs(net);
     return K2Y_OK;
 }

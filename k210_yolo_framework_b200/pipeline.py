@@ -45,6 +45,7 @@ class DetectionPipeline:
         self._stage_free = [torch.cuda.Event() for _ in range(2)]
         self._d2h_done = [torch.cuda.Event() for _ in range(2)]
         self._submitted = 0
+        self._stage_u8 = None
 
     def set_image_shapes(self, image_hw) -> None:
         """Original (pre-letterbox) image sizes, [batch, 2] (h, w); defaults to the network input size."""
@@ -60,10 +61,14 @@ class DetectionPipeline:
         return self.gather.gather()
 
     def detect_host(self, x_host: torch.Tensor):
-        """x_host: CPU float32 [batch,H,W,3] tensor (pinned for an asynchronous copy).  Returns host tensors
-        (dets, counts) for all images of the job, after a stream synchronise."""
+        """x_host: CPU float32 (normalised) or uint8 (raw letterboxed RGB) [batch,H,W,3] tensor, pinned for an
+        asynchronous copy.  Returns host tensors (dets, counts) for all images of the job, after a stream synchronise."""
         n = x_host.shape[0]
-        self.engine.input_buffer[:n].copy_(x_host, non_blocking=True)
+        if x_host.dtype == torch.uint8:
+            self.engine.enable_u8_input()[:n].copy_(x_host, non_blocking=True)
+        else:
+            self.engine.disable_u8_input()
+            self.engine.input_buffer[:n].copy_(x_host, non_blocking=True)
         dets, counts = self.step_device(n)
         self._host_dets.copy_(dets, non_blocking=True)
         self._host_counts.copy_(counts, non_blocking=True)
@@ -78,12 +83,21 @@ class DetectionPipeline:
         slot = self._submitted % 2
         self._submitted += 1
         compute = torch.cuda.current_stream(self.device_index)
+        u8 = x_host.dtype == torch.uint8
+        if u8:  # raw letterboxed RGB: 4x fewer PCIe bytes, normalisation (img / max(img)) fused into the first conv
+            if self._stage_u8 is None:
+                self._stage_u8 = [torch.empty(self.engine.input_buffer.shape, dtype=torch.uint8, device=self.engine.input_buffer.device)
+                                  for _ in range(2)]
+            stage, dst = self._stage_u8[slot], self.engine.enable_u8_input()
+        else:
+            self.engine.disable_u8_input()
+            stage, dst = self._stage[slot], self.engine.input_buffer
         self._copy_stream.wait_event(self._stage_free[slot])
         with torch.cuda.stream(self._copy_stream):
-            self._stage[slot][:n].copy_(x_host, non_blocking=True)
+            stage[:n].copy_(x_host, non_blocking=True)
             self._h2d_done[slot].record(self._copy_stream)
         compute.wait_event(self._h2d_done[slot])
-        self.engine.input_buffer[:n].copy_(self._stage[slot][:n], non_blocking=True)
+        dst[:n].copy_(stage[:n], non_blocking=True)
         self._stage_free[slot].record(compute)
         dets, counts = self.step_device(n)
         self._slot_dets[slot].copy_(dets, non_blocking=True)

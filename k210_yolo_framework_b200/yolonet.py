@@ -160,6 +160,35 @@ class YoloEngine:
         check(lib.k2y_net_bind(self._h, self._ws.data_ptr(), self._ws.numel(), self._x.data_ptr(), ptrs, len(self._heads)))
         self._bound = True
 
+    def enable_u8_input(self) -> torch.Tensor:
+        """Switch the network to the uint8 front end (k2y_net_bind_u8): returns the bound device buffer
+        [max_batch,H,W,3] uint8 (letterboxed RGB).  ``img / np.max(img)`` (tools/utils.py:405) then happens on the GPU."""
+        self._bind()
+        if getattr(self, "_x_u8", None) is None:
+            dev = torch.device("cuda", self.device_index)
+            self._x_u8 = torch.empty((self.max_batch, self.in_h, self.in_w, 3), dtype=torch.uint8, device=dev)
+            self._img_max = torch.zeros((self.max_batch,), dtype=torch.int32, device=dev)
+        check(lib.k2y_net_bind_u8(self._h, self._x_u8.data_ptr(), self._img_max.data_ptr()))
+        self._u8_on = True
+        return self._x_u8
+
+    def disable_u8_input(self) -> None:
+        if getattr(self, "_u8_on", False):
+            check(lib.k2y_net_bind_u8(self._h, None, None))
+            self._u8_on = False
+
+    def predict_device_u8(self, x_u8: torch.Tensor) -> List[torch.Tensor]:
+        """x_u8: CUDA uint8 [N,H,W,3].  Same result as predict_device(x_u8 / max(x_u8) per image)."""
+        if x_u8.dim() != 4 or tuple(x_u8.shape[1:]) != (self.in_h, self.in_w, 3) or x_u8.dtype != torch.uint8 or not x_u8.is_cuda:
+            raise ValueError(f"expected CUDA uint8 [N,{self.in_h},{self.in_w},3]")
+        n = x_u8.shape[0]
+        if n > self.max_batch:
+            raise ValueError(f"batch {n} > max_batch {self.max_batch}")
+        buf = self.enable_u8_input()
+        if x_u8.data_ptr() != buf.data_ptr():
+            buf[:n].copy_(x_u8, non_blocking=True)
+        return self.run(n)
+
     @property
     def input_buffer(self) -> torch.Tensor:
         """The bound device input [max_batch, H, W, 3] f32 — write into it to skip the staging copy."""
@@ -188,6 +217,7 @@ class YoloEngine:
         if n > self.max_batch:
             raise ValueError(f"batch {n} > max_batch {self.max_batch}")
         self._bind()
+        self.disable_u8_input()
         if x.data_ptr() != self._x.data_ptr():
             self._x[:n].copy_(x, non_blocking=True)
         return self.run(n)

@@ -46,3 +46,25 @@ def test_host_and_streaming_api_match_oracle(golden_weights, voc_anchors, dog_u8
     assert outs[0] == got and outs[2] == got
     assert outs[1] == got[::-1]
     assert pipe.launches_per_step() >= 33
+
+
+def test_uint8_front_end_is_bit_identical(golden_weights, voc_anchors, dog_u8):
+    """uint8 input + on-GPU `img / np.max(img)` == feeding the float32 array the reference builds on the host."""
+    n = 4
+    pipe = DetectionPipeline("yolo_mobilev1", (224, 320), voc_anchors, 20, 0.75, n, obj_thresh=0.7, iou_thresh=0.5)
+    pipe.engine.set_weights(golden_weights)
+    imgs = [dog_u8, dog_u8[::-1].copy(), (dog_u8 // 2).astype(np.uint8), np.roll(dog_u8, 40, axis=1)]   # image 2 has max 127
+    u8 = np.stack(imgs)
+    f32 = np.stack([(im / np.max(im)).astype(np.float32) for im in imgs])
+    heads_f = [t.clone() for t in pipe.engine.predict_device(torch.from_numpy(f32).cuda())]
+    heads_u = [t.clone() for t in pipe.engine.predict_device_u8(torch.from_numpy(u8).cuda())]
+    for a, b in zip(heads_f, heads_u):
+        assert torch.equal(a, b)
+    d_u, c_u = pipe.detect_host(torch.from_numpy(u8).pin_memory())
+    got_u = DetectionPipeline.records(d_u.clone(), c_u.clone())
+    d_f, c_f = pipe.detect_host(torch.from_numpy(f32).pin_memory())
+    assert DetectionPipeline.records(d_f.clone(), c_f.clone()) == got_u
+    assert [(d[0], d[1]) for d in got_u[0]] == [(6, 53), (11, 765)]
+    tk = pipe.submit(torch.from_numpy(u8).pin_memory())
+    d_s, c_s = pipe.collect(tk)
+    assert DetectionPipeline.records(d_s.clone(), c_s.clone()) == got_u
