@@ -1,16 +1,18 @@
 // Fused decode + per-class greedy NMS, both dialects of the reference:
 //   KERAS    keras_inference.py:94-135 (+ tools/utils.py:524-547, keras_inference.py:32-72)
 //   REGION_C yolo3_frame_test_public/region_layer.c:121-283
-// One CTA per image.  Phase 1 (all threads): sigmoid/exp/anchor-scale decode of every box, scores
-// written class-major so that phase 2 scans them coalesced.  Phase 2 (one warp per class):
-// ballot-compaction of the candidates in index order, warp bitonic sort on (score desc, index asc)
-// keys, then greedy IoU suppression with the selected boxes held one per lane, so that testing a
-// candidate against <= 32 kept boxes is a single ballot.  Final records are written contiguously
-// per (image, class).
+// KERAS: one warp per (image, class): scan of the head tensors (score = sigmoid(cls) * sigmoid(conf)) with
+// ballot-compaction of the candidates in index order, register-resident bitonic sort on (score desc, index asc)
+// keys, then greedy IoU suppression resolved 32 candidates at a time (kept boxes and the chunk's candidates cached
+// (min,max)-normalised in shared memory, intra-chunk suppression as bitmasks).  REGION_C: one CTA per image (softmax +
+// decode by all threads, then one warp per class).  Final records are written contiguously per (image, class).
 //
 // Arithmetic is float32 in the reference's operation order with explicit round-to-nearest
 // intrinsics where FMA contraction would change a rounding, so survivor sets are bit-identical to
 // the oracle's whenever the transcendental results (expf) agree.
+#include <cstdlib>
+#include <vector>
+
 #include "common.h"
 
 namespace k2y {
@@ -45,6 +47,53 @@ __device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long 
         }
     }
     return key;
+}
+
+// Bitonic sort (descending) of 32*R keys held R per lane, element e = r*32 + lane.  Exchanges at distance >= 32 are
+// register-to-register inside a lane, shorter ones are warp shuffles; everything is unrolled, so the keys never leave
+// the register file (the in-memory version below cost ~100 cycles per compare-exchange on the critical path).
+template <int R>
+__device__ __forceinline__ void warp_sort_desc_regs(unsigned long long (&key)[R], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rj) == 0) {
+                        const bool desc = ((r * 32) & k) == 0;  // k >= 64 here: decided by the register index alone
+                        const unsigned long long a = key[r], b = key[r ^ rj];
+                        const unsigned long long mx = a > b ? a : b, mn = a > b ? b : a;
+                        key[r] = desc ? mx : mn;
+                        key[r ^ rj] = desc ? mn : mx;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned long long other = __shfl_xor_sync(FULL, key[r], j);
+                    const bool desc = (((r * 32 + lane) & k) == 0);
+                    const bool lower = ((lane & j) == 0);
+                    const bool take_max = (desc == lower);
+                    key[r] = take_max ? (key[r] > other ? key[r] : other) : (key[r] < other ? key[r] : other);
+                }
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void warp_sort_desc_via_regs(unsigned long long *keys, int n, int lane) {
+    unsigned long long k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = (r * 32 + lane < n) ? keys[r * 32 + lane] : 0ull;
+    warp_sort_desc_regs<R>(k, lane);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) keys[r * 32 + lane] = k[r];
+    __syncwarp();
 }
 
 // Bitonic sort (descending) of P (power of two) keys in memory by one warp.
@@ -105,6 +154,31 @@ __device__ __forceinline__ bool iou_yxyx_gt(const float4 a, const float4 b, floa
     return __fdiv_rn(inter, uni) > thr;
 }
 
+// Same predicate on boxes already (min,max)-normalised with their areas cached (computed exactly as above, once per
+// box instead of once per pair).
+__device__ __forceinline__ float4 norm_box(const float4 a, float &area) {
+    float4 n;
+    n.x = fminf(a.x, a.z);
+    n.y = fminf(a.y, a.w);
+    n.z = fmaxf(a.x, a.z);
+    n.w = fmaxf(a.y, a.w);
+    area = __fmul_rn(__fsub_rn(n.z, n.x), __fsub_rn(n.w, n.y));
+    return n;
+}
+__device__ __forceinline__ bool iou_norm_gt(const float4 a, float area_a, const float4 b, float area_b, float thr) {
+    if (area_a <= 0.f || area_b <= 0.f) return 0.f > thr;
+    const float iy = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+    const float ix = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+    const float inter = __fmul_rn(iy, ix);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    if (thr >= 0.f && uni > 0.f) {
+        const float t = __fmul_rn(thr, uni);
+        if (inter > __fmul_rn(t, 1.000001f)) return true;
+        if (inter < __fmul_rn(t, 0.999999f)) return false;
+    }
+    return __fdiv_rn(inter, uni) > thr;
+}
+
 // region_layer.c box_iou on centre-form (x,y,w,h) boxes (:228-254).
 __device__ __forceinline__ float overlap_c(float x1, float w1, float x2, float w2) {
     const float l1 = __fsub_rn(x1, __fmul_rn(w1, 0.5f));
@@ -136,6 +210,7 @@ struct KerasParams {
     int *counts;
     unsigned long long *keys_global;  // [B][C][P] — only used when P does not fit shared memory
     int keys_in_smem;
+    long long *trace;                 // optional [B][C][4]: cycles of scan / sort / nms and the candidate count (K2Y_DET_TRACE=1)
 };
 
 // Collects the candidates of one class (score passes `pred`) in index order, sorts them.
@@ -225,6 +300,7 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const Kera
     x.sc_x = __fdiv_rn(p.in_w, new_w);
 
     // ---- scan: candidates of class c in index order (4 x 32 boxes per step so that the loads overlap) ----
+    const long long tc0 = p.trace ? clock64() : 0;
     int n = 0;
     for (int base = 0; base < p.nbox; base += 128) {
         float lc[4], lk[4];
@@ -234,8 +310,11 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const Kera
             lc[u] = 0.f;
             lk[u] = 0.f;
             if (box < p.nbox) {
-                int l, a, col, row;
-                const float *e = box_entry(p, b, box, l, a, col, row);
+                // entry pointer needs no (row, col, anchor) split: boxes of a layer are contiguous [cell][anchor] records
+                int l = 0;
+                if (p.n_layers > 1 && box >= p.loff[1]) l = 1;
+                if (p.n_layers > 2 && box >= p.loff[2]) l = 2;
+                const float *e = p.heads[l] + ((size_t)b * (p.loff[l + 1] - p.loff[l]) + (box - p.loff[l])) * (5 + p.C);
                 lc[u] = __ldg(e + 4);
                 lk[u] = __ldg(e + 5 + c);
             }
@@ -255,10 +334,21 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const Kera
         }
     }
     __syncwarp();
+    const long long tc1 = p.trace ? clock64() : 0;
     unsigned long long rkey = 0ull;
     if (n <= 32) {
         if (lane < n) rkey = keys[lane];
         rkey = warp_sort_desc(rkey, lane);
+    } else if (n <= 64) {
+        warp_sort_desc_via_regs<2>(keys, n, lane);
+    } else if (n <= 128) {
+        warp_sort_desc_via_regs<4>(keys, n, lane);
+    } else if (n <= 256) {
+        warp_sort_desc_via_regs<8>(keys, n, lane);
+    } else if (n <= 512) {
+        warp_sort_desc_via_regs<16>(keys, n, lane);
+    } else if (n <= 1024 && p.P >= 1024) {
+        warp_sort_desc_via_regs<32>(keys, n, lane);
     } else {
         int P = 64;
         while (P < n) P <<= 1;
@@ -267,62 +357,86 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const Kera
         warp_sort_desc_mem(keys, P, lane);
     }
 
+    const long long tc2 = p.trace ? clock64() : 0;
     // ---- greedy NMS over the sorted candidates, 32 at a time ----
     // Per chunk: (a) every lane tests ITS candidate against the boxes kept so far, (b) every lane computes the bitmask
     // of later candidates of the chunk its box would suppress, (c) a short warp-uniform scan over the chunk resolves
     // the greedy order from the masks.  The IoU work is thereby done 32-wide instead of one candidate at a time;
     // the result is exactly the sequential algorithm's (a candidate is kept iff no earlier KEPT box overlaps it).
     k2y_det *out = p.dets + ((size_t)b * p.C + c) * p.maxk;
-    float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f);  // lane s holds kept box s (first 32)
+    __shared__ float4 s_kbox[DET_WARPS][32], s_cbox[DET_WARPS][32];   // kept / candidate boxes, (min,max)-normalised
+    __shared__ float s_karea[DET_WARPS][32], s_carea[DET_WARPS][32];
+    __shared__ float4 s_orig[DET_WARPS][32];            // candidate boxes as decoded (the records keep these)
+    __shared__ unsigned long long s_key[DET_WARPS][32];
+    __shared__ unsigned s_mask[DET_WARPS][32];
+    float4 *kbox = s_kbox[warp], *cbox = s_cbox[warp];
+    float *karea = s_karea[warp], *carea = s_carea[warp];
     int nsel = 0;
+    long long t_dec = 0, t_a = 0, t_b = 0, t_c = 0;
     for (int base = 0; base < n && nsel < p.maxk; base += 32) {
+        const long long q0 = p.trace ? clock64() : 0;
         const int i = base + lane;
         const unsigned long long mykey = (n <= 32) ? rkey : (i < n ? keys[i] : 0ull);
         const int cnt = min(32, n - base);
         float4 cand = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) cand = decode_box(p, x, b, key_index(mykey));
-        // (a) against the kept set
+        float my_area;
+        const float4 my = norm_box(cand, my_area);
+        cbox[lane] = my;
+        carea[lane] = my_area;
+        __syncwarp();
+        const long long q1 = p.trace ? clock64() : 0;
+        // (a) against the kept set: two kept boxes per step (independent chains), stop as soon as the chunk is dead
         bool dead = lane >= cnt;
         const int nreg = min(nsel, 32);
-        for (int s2 = 0; s2 < nreg; ++s2) {
-            float4 kb;
-            kb.x = __shfl_sync(FULL, mybox.x, s2);
-            kb.y = __shfl_sync(FULL, mybox.y, s2);
-            kb.z = __shfl_sync(FULL, mybox.z, s2);
-            kb.w = __shfl_sync(FULL, mybox.w, s2);
-            if (!dead && iou_yxyx_gt(cand, kb, p.iou)) dead = true;
+        for (int s2 = 0; s2 < nreg; s2 += 4) {  // four independent IoU chains per step
+            if (__ballot_sync(FULL, !dead) == 0u) break;
+            bool hit = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int si = s2 + u < nreg ? s2 + u : s2;
+                hit |= iou_norm_gt(my, my_area, kbox[si], karea[si], p.iou);
+            }
+            dead = dead || hit;
         }
         for (int s2 = 32; s2 < nsel; ++s2) {  // only when max_per_class > 32
             const k2y_det d = out[s2];
             if (!dead && iou_yxyx_gt(cand, make_float4(d.ymin, d.xmin, d.ymax, d.xmax), p.iou)) dead = true;
         }
-        // (b) suppression masks inside the chunk — only candidates that survived (a) can suppress anything,
-        //     so the loop runs over the set bits of `alive` (usually a handful) instead of all 32 lanes
+        const long long q2 = p.trace ? clock64() : 0;
+        // (b) suppression masks inside the chunk — only candidates that survived (a) can suppress anything
         const unsigned alive = ~__ballot_sync(FULL, dead);
         unsigned mask = 0u;
-        for (unsigned mm = alive; mm; mm &= mm - 1u) {
-            const int j = __ffs(mm) - 1;
-            float4 ob;
-            ob.x = __shfl_sync(FULL, cand.x, j);
-            ob.y = __shfl_sync(FULL, cand.y, j);
-            ob.z = __shfl_sync(FULL, cand.z, j);
-            ob.w = __shfl_sync(FULL, cand.w, j);
-            if (j > lane && !dead && iou_yxyx_gt(ob, cand, p.iou)) mask |= 1u << j;
+        for (unsigned mm = alive; mm;) {
+            const int j0 = __ffs(mm) - 1;
+            mm &= mm - 1u;
+            const int j1 = mm ? __ffs(mm) - 1 : j0;
+            mm &= mm - 1u;
+            const bool h0 = iou_norm_gt(cbox[j0], carea[j0], my, my_area, p.iou);
+            const bool h1 = iou_norm_gt(cbox[j1], carea[j1], my, my_area, p.iou);
+            if (!dead) {
+                if (j0 > lane && h0) mask |= 1u << j0;
+                if (j1 > lane && h1) mask |= 1u << j1;
+            }
         }
-        // (c) resolve in score order
+        s_mask[warp][lane] = mask;
+        s_key[warp][lane] = mykey;
+        s_orig[warp][lane] = cand;
+        __syncwarp();
+        const long long q3 = p.trace ? clock64() : 0;
+        // (c) resolve in score order — a short warp-uniform scan; lane 0 records the survivors
         unsigned remv = ~alive;
         for (unsigned mm = alive; mm && nsel < p.maxk; mm &= mm - 1u) {
             const int j = __ffs(mm) - 1;
             if ((remv >> j) & 1u) continue;
-            float4 kb;
-            kb.x = __shfl_sync(FULL, cand.x, j);
-            kb.y = __shfl_sync(FULL, cand.y, j);
-            kb.z = __shfl_sync(FULL, cand.z, j);
-            kb.w = __shfl_sync(FULL, cand.w, j);
-            const unsigned long long key = __shfl_sync(FULL, mykey, j);
-            remv |= __shfl_sync(FULL, mask, j);
-            if (lane == nsel) mybox = kb;
+            remv |= s_mask[warp][j];
             if (lane == 0) {
+                if (nsel < 32) {
+                    kbox[nsel] = cbox[j];
+                    karea[nsel] = carea[j];
+                }
+                const float4 kb = s_orig[warp][j];
+                const unsigned long long key = s_key[warp][j];
                 k2y_det d;
                 d.ymin = kb.x;
                 d.xmin = kb.y;
@@ -335,8 +449,22 @@ __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const Kera
             ++nsel;
         }
         __syncwarp();
+        if (p.trace) {
+            const long long q4 = clock64();
+            t_dec += q1 - q0;
+            t_a += q2 - q1;
+            t_b += q3 - q2;
+            t_c += q4 - q3;
+        }
     }
     if (lane == 0) p.counts[b * p.C + c] = nsel;
+    if (p.trace && lane == 0) {
+        long long *o = p.trace + ((size_t)b * p.C + c) * 4;
+        o[0] = tc1 - tc0;
+        o[1] = tc2 - tc1;
+        o[2] = clock64() - tc2;
+        o[3] = n;
+    }
 }
 
 struct RegionParams {
@@ -515,8 +643,34 @@ extern "C" int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *h
         attr_set = true;
     }
     dim3 grid((p.C + DET_WARPS - 1) / DET_WARPS, batch);
+    p.trace = nullptr;
+    const char *tr = getenv("K2Y_DET_TRACE");
+    if (tr && tr[0] == '1') {
+        K2Y_CUDA_CHECK(cudaMalloc(&p.trace, (size_t)batch * p.C * 4 * sizeof(long long)));
+        K2Y_CUDA_CHECK(cudaMemset(p.trace, 0, (size_t)batch * p.C * 4 * sizeof(long long)));
+    }
     detect_keras_kernel<<<grid, DET_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
     K2Y_CUDA_CHECK(cudaGetLastError());
+    if (p.trace) {
+        K2Y_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+        std::vector<long long> h((size_t)batch * p.C * 4);
+        cudaMemcpy(h.data(), p.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(p.trace);
+        long long mx[4] = {0, 0, 0, 0};
+        double sum[4] = {0, 0, 0, 0};
+        size_t worst = 0;
+        for (size_t i = 0; i < (size_t)batch * p.C; ++i) {
+            for (int j = 0; j < 4; ++j) {
+                sum[j] += (double)h[i * 4 + j];
+                if (h[i * 4 + j] > mx[j]) mx[j] = h[i * 4 + j];
+            }
+            if (h[i * 4] + h[i * 4 + 1] + h[i * 4 + 2] > h[worst * 4] + h[worst * 4 + 1] + h[worst * 4 + 2]) worst = i;
+        }
+        const double cnt = (double)batch * p.C;
+        fprintf(stderr, "[det-trace] cycles mean (scan %.0f sort %.0f nms %.0f n %.1f) max (scan %lld sort %lld nms %lld n %lld) worst warp: scan %lld sort %lld nms %lld n %lld\n",
+                sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, mx[0], mx[1], mx[2], mx[3], h[worst * 4], h[worst * 4 + 1],
+                h[worst * 4 + 2], h[worst * 4 + 3]);
+    }
     return K2Y_OK;
 }
 
