@@ -331,8 +331,14 @@ def run_ours(args):
             det_ms += ev0.elapsed_time(ev1) / reps
         top = max(acc, key=lambda a: a["ms"])
         tf32_note = "tensor peak = measured dense bf16 (cuBLAS); the bf16x3 split scheme issues 3 MMAs per useful MAC, so it tops out at 1/3 of it"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(top["name"])
         roof = {"kernel": top["name"], "bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "traffic": None, "peak_source": peaks["source"],
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "traffic": traffic, "peak_source": peaks["source"],
+                "algorithmic_bytes": top["bytes"], "hbm_gbs_if_memory_bound": top["bytes"] / (top["ms"] * 1e-3) / 1e9,
                 "launch_ms": top["ms"], "share_of_net": top["ms"] / net_ms, "note": tf32_note}
         roof["frac"] = roof["achieved"] / roof["peak"]
         layer_roof = sum(max(a["flops"] / (peaks["bf16_tflops"] * 1e12), a["bytes"] / (peaks["hbm_gbs"] * 1e9)) for a in acc) * 1e3
