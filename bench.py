@@ -336,10 +336,16 @@ def run_ours(args):
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get(top["name"])
-        roof = {"kernel": top["name"], "bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "traffic": traffic, "peak_source": peaks["source"],
-                "algorithmic_bytes": top["bytes"], "hbm_gbs_if_memory_bound": top["bytes"] / (top["ms"] * 1e-3) / 1e9,
-                "launch_ms": top["ms"], "share_of_net": top["ms"] / net_ms, "note": tf32_note}
+        t_tensor = top["flops"] / (peaks["bf16_tflops"] * 1e12)
+        t_hbm = top["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        if t_tensor >= t_hbm:
+            roof = {"kernel": top["name"], "bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12,
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "note": tf32_note}
+        else:
+            roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "note": "algorithmic bytes = fp32 activations read once + written once"}
+        roof.update({"traffic": traffic, "peak_source": peaks["source"], "launch_ms": top["ms"], "share_of_net": top["ms"] / net_ms,
+                     "algorithmic_flops": top["flops"], "algorithmic_bytes": top["bytes"]})
         roof["frac"] = roof["achieved"] / roof["peak"]
         layer_roof = sum(max(a["flops"] / (peaks["bf16_tflops"] * 1e12), a["bytes"] / (peaks["hbm_gbs"] * 1e9)) for a in acc) * 1e3
         ms_per_step = dev_ms / args.steps
