@@ -197,6 +197,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -269,6 +270,7 @@ struct TcParams {
     int a_boxes;                    // 16 KB sub-tiles of raw fp32 A per stage (k per k-block / 32)
     uint32_t tmem_cols;
     float act_slope, act_clamp;     // branch-free activation parameters
+    int epi_groups;                 // 1, or 2: the idle gather warps form a second epilogue group (plain 1x1 convs)
     int tma_store;                  // 1: epilogue writes through a TMA store (N % 4 == 0, no residual)
     int dbg;                        // bring-up switches (K2Y_TC_DBG): 1 skip stores, 2 skip tmem loads, 4 skip convert math
     long long *trace;               // optional [gridDim.x][16] globaltimer stamps (K2Y_TC_TRACE=1 via k2y_conv2d)
@@ -290,7 +292,7 @@ struct __align__(8) Barriers {
     uint32_t tmem_slot;
 };
 // dynamic smem besides the stage ring: alignment slack, barriers, epilogue staging (2 x 4 KB per epilogue warp)
-constexpr size_t FIXED_SMEM = 1024 + sizeof(Barriers) + 1024 + 4 * 8192 + 4096;  // + double-buffered scale/shift of a tile
+constexpr size_t FIXED_SMEM = 1024 + sizeof(Barriers) + 1024 + 4 * 8192 + 2 * 4096;  // + scale/shift copies of two epilogue groups
 
 template <bool GATHER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -325,7 +327,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&bars->tmem_full[a]), 1);
-            mbar_init(smem_u32(&bars->tmem_empty[a]), 128);
+            mbar_init(smem_u32(&bars->tmem_empty[a]), 128u * (uint32_t)p.epi_groups);
         }
         fence_barrier_init();
         if (!GATHER) prefetch_tmap(&map_a);
@@ -348,6 +350,174 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // tensor-memory columns: [0, 2*BN) two accumulators, then per stage 32 columns of A_hi and 32 of A_lo
     auto tmem_a_hi = [&](int s) { return tmem_base + 2u * (uint32_t)p.BN + (uint32_t)s * 64u; };
     auto stage_b_lo = [&](int s) { return stage_b_hi(s) + b_bytes; };
+
+    // ================= epilogue (a lambda: run by warps 10-13, and by the idle gather warps 2-5 as a second group when the
+    // conv is a plain 1x1 — the early pointwise layers are epilogue-bound, two groups split a tile's 32-column chunks) ====
+    auto epilogue = [&](const int g, const int ew) {
+        // ================= epilogue =================
+        // TMEM -> registers (lane = GEMM row) -> BN-fold/activation -> 128B-swizzled smem staging [32 rows][32 cols]
+        // per warp -> either one TMA store per 32-column chunk (full-line writes, no LSU work) or, for N % 4 != 0 /
+        // residual layers, row-contiguous st.global (a warp instruction covers 4 rows x 128 contiguous bytes).
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const bool n_vec = (p.N & 3) == 0;
+        // two 4 KB staging buffers per warp, 1024-byte aligned (SWIZZLE_128B atom)
+        // staging: 32 KB after the barriers.  One epilogue group: 2 x 4 KB per warp (double buffered against its TMA store);
+        // two groups: 4 KB per warp each.  Then one 4 KB scale/shift copy per group (double buffered by tile parity).
+        const int ng = p.epi_groups;
+        const uint32_t epi_base = (smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)sizeof(Barriers) + 1023u) & ~1023u;
+        const uint32_t stg_base = ng == 1 ? epi_base + (uint32_t)ew * 8192u : epi_base + (uint32_t)g * 16384u + (uint32_t)ew * 4096u;
+        const uint32_t ss_base = epi_base + 32768u + (uint32_t)g * 4096u;
+        const bool tracer = g == 0 && ew == 0 && lane == 0;
+        const int chunk = lane & 7, rsub = lane >> 3;
+        uint32_t acc_it = 0, stg_it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++acc_it) {
+            const int ks = t % p.k_splits, tt = t / p.k_splits;
+            const int mp = tt / p.n_tiles, nt = tt - mp * p.n_tiles;
+            const int mt = mp * p.cluster + crank;
+            const bool tile_ok = mt < p.m_tiles;  // odd m-tile count: the pair's second CTA only helps with the weights
+            const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+            // With ~227 KB of shared memory carved out there is practically no L1 left, so per-column scale/shift loads
+            // were L2 round trips on the epilogue's critical path: stage the tile's BN columns in shared memory (double
+            // buffered by tile parity) while the mainloop of this tile is still running.
+            const uint32_t ss = ss_base + (acc_it & 1u) * 2048u;
+            {
+                const int et = ew * 32 + lane;  // 0..127 inside the group
+                for (int j = et; j < ((p.BN + 31) & ~31); j += 128) {
+                    const int n = nt * p.BN + j;
+                    const bool in = j < p.BN && n < p.N;
+                    const float scv = in ? __ldg(p.scale + n) : 0.f, shv = in ? __ldg(p.shift + n) : 0.f;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss + (uint32_t)j * 4u), "f"(scv) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss + 1024u + (uint32_t)j * 4u), "f"(shv) : "memory");
+                }
+                if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of this epilogue group only
+                else asm volatile("bar.sync 3, 128;" ::: "memory");
+            }
+            mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
+            if (t == cluster_id && tracer) K2Y_TRACE(8);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)p.BN;
+            // split-K partials of slice ks live at rows [ks * m_tiles * 128, ...) of the scratch tensor
+            const int m_base = (ks * p.m_tiles + mt) * BM + q * 32;
+            for (int c0 = g * 32; c0 < p.BN; c0 += 32 * ng, ++stg_it) {
+                const int ncols = (p.BN - c0) < 32 ? (p.BN - c0) : 32;  // 32 or 16
+                const int n0 = nt * p.BN + c0;
+                const uint32_t stg = stg_base + (ng == 1 ? (stg_it & 1u) * 4096u : 0u);
+                uint32_t r[32];
+                const bool tr = p.trace && t == cluster_id && c0 == 32 && tracer;
+                long long c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_4 = 0;
+                if (tr) c_0 = clock64();
+                tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                if (ncols == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+                else {
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) r[j] = 0u;
+                }
+                tmem_ld_wait();
+                if (tr) c_1 = clock64();
+                if (p.tma_store) {
+                    // scale/shift come from the shared-memory copy (zero beyond N, so no bounds checks); the activation is
+                    // specialised outside the element loop: leaky = max(v, slope*v), relu = max(v,0), relu6 = min(max(v,0),6)
+#define K2Y_EPI_LOOP(ACT_EXPR)                                                                                     \
+    _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                                             \
+        const float4 s4 = ld_shared_v4(ss + (uint32_t)(c0 + j) * 4u);                                               \
+        const float4 h4 = ld_shared_v4(ss + 1024u + (uint32_t)(c0 + j) * 4u);                                       \
+        float v;                                                                                                     \
+        v = fmaf(__uint_as_float(r[j]), s4.x, h4.x);     r[j] = __float_as_uint(ACT_EXPR);                           \
+        v = fmaf(__uint_as_float(r[j + 1]), s4.y, h4.y); r[j + 1] = __float_as_uint(ACT_EXPR);                       \
+        v = fmaf(__uint_as_float(r[j + 2]), s4.z, h4.z); r[j + 2] = __float_as_uint(ACT_EXPR);                       \
+        v = fmaf(__uint_as_float(r[j + 3]), s4.w, h4.w); r[j + 3] = __float_as_uint(ACT_EXPR);                       \
+    }
+                    if (p.act == ACT_LEAKY) {
+                        const float slope = p.act_slope;
+                        K2Y_EPI_LOOP(fmaxf(v, v * slope))
+                    } else if (p.act == ACT_RELU) {
+                        K2Y_EPI_LOOP(fmaxf(v, 0.f))
+                    } else if (p.act == ACT_RELU6) {
+                        K2Y_EPI_LOOP(fminf(fmaxf(v, 0.f), 6.f))
+                    } else {
+                        K2Y_EPI_LOOP(v)
+                    }
+#undef K2Y_EPI_LOOP
+                    if (tr) c_2 = clock64();
+                    // the staging buffer used two chunks ago must have been read by its TMA store
+                    if (lane == 0) {
+                        if (ng == 1) tma_store_wait_read1();
+                        else tma_store_wait_read0();
+                    }
+                    __syncwarp();
+                    if (tr) c_3 = clock64();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[j * 4], r[j * 4 + 1],
+                                     r[j * 4 + 2], r[j * 4 + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (tr) c_4 = clock64();
+                    if (lane == 0 && tile_ok && !(p.dbg & 1)) {
+                        tma_store_2d(&map_out, stg, n0, m_base);  // rows >= M and columns >= N are clipped by the TMA
+                        tma_store_commit();
+                    }
+                    if (tr) {
+                        long long *o = p.trace + (size_t)blockIdx.x * 64 + 48;
+                        o[0] = c_1 - c_0;
+                        o[1] = c_2 - c_1;
+                        o[2] = c_3 - c_2;
+                        o[3] = c_4 - c_3;
+                        o[4] = clock64() - c_4;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[j * 4], r[j * 4 + 1],
+                                     r[j * 4 + 2], r[j * 4 + 3]);
+                    __syncwarp();
+                    const int n = n0 + chunk * 4;
+                    const bool col_ok = (chunk * 4 < ncols) && (n < p.N);
+                    const bool full4 = n_vec && (n + 3 < p.N);
+                    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (n + j < p.N) {
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc[j]) : "r"(ss + (uint32_t)(c0 + chunk * 4 + j) * 4u));
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sh[j]) : "r"(ss + 1024u + (uint32_t)(c0 + chunk * 4 + j) * 4u));
+                            }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + rsub;
+                        const int m = m_base + row;
+                        const float4 v = ld_shared_v4(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
+                        if (col_ok && tile_ok && m < p.M && !(p.dbg & 1)) {
+                            float o[4];
+                            o[0] = act_bf(fmaf(v.x, sc[0], sh[0]), p.act_slope, p.act_clamp);
+                            o[1] = act_bf(fmaf(v.y, sc[1], sh[1]), p.act_slope, p.act_clamp);
+                            o[2] = act_bf(fmaf(v.z, sc[2], sh[2]), p.act_slope, p.act_clamp);
+                            o[3] = act_bf(fmaf(v.w, sc[3], sh[3]), p.act_slope, p.act_clamp);
+                            float *out = p.dst + (size_t)m * p.N + n;
+                            if (full4) {
+                                if (p.residual) {
+                                    const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + (size_t)m * p.N + n));
+                                    o[0] += rr.x, o[1] += rr.y, o[2] += rr.z, o[3] += rr.w;
+                                }
+                                *reinterpret_cast<float4 *>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (n + j < p.N) out[j] = o[j] + (p.residual ? __ldg(p.residual + (size_t)m * p.N + n + j) : 0.f);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->tmem_empty[a]));
+            if (t == cluster_id && tracer) K2Y_TRACE(9);
+        }
+        if (p.tma_store && lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
+        if (tracer) K2Y_TRACE(10);
+    };
 
     if (warp == 0) {
         // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
@@ -458,6 +628,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // computes the source address of GEMM row r once per k-block; the addresses are then exchanged with warp shuffles
         // so that 8 (tf32) or 16 (bf16) consecutive lanes copy one row's run: a cp.async warp instruction touches 4 or 2
         // full 128-byte lines instead of 32 different ones (the L1/LSU request rate was the limiter of the 3x3 convs).
+        if (!GATHER && p.epi_groups == 2) epilogue(1, warp - 2);
         if (GATHER) {
             const int r = threadIdx.x - 64;  // GEMM row inside the tile, 0..127
             const int Cin = p.C0 + p.C1;
@@ -603,161 +774,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ================= epilogue =================
-        // TMEM -> registers (lane = GEMM row) -> BN-fold/activation -> 128B-swizzled smem staging [32 rows][32 cols]
-        // per warp -> either one TMA store per 32-column chunk (full-line writes, no LSU work) or, for N % 4 != 0 /
-        // residual layers, row-contiguous st.global (a warp instruction covers 4 rows x 128 contiguous bytes).
-        const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const bool n_vec = (p.N & 3) == 0;
-        // two 4 KB staging buffers per warp, 1024-byte aligned (SWIZZLE_128B atom)
-        const uint32_t stg_base = ((smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)sizeof(Barriers) + 1023u) & ~1023u) +
-                                  (uint32_t)(warp - 10) * 8192u;
-        const uint32_t ss_base = ((smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)sizeof(Barriers) + 1023u) & ~1023u) + 4u * 8192u;
-        const int chunk = lane & 7, rsub = lane >> 3;
-        uint32_t acc_it = 0, stg_it = 0;
-        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++acc_it) {
-            const int ks = t % p.k_splits, tt = t / p.k_splits;
-            const int mp = tt / p.n_tiles, nt = tt - mp * p.n_tiles;
-            const int mt = mp * p.cluster + crank;
-            const bool tile_ok = mt < p.m_tiles;  // odd m-tile count: the pair's second CTA only helps with the weights
-            const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-            // With ~227 KB of shared memory carved out there is practically no L1 left, so per-column scale/shift loads
-            // were L2 round trips on the epilogue's critical path: stage the tile's BN columns in shared memory (double
-            // buffered by tile parity) while the mainloop of this tile is still running.
-            const uint32_t ss = ss_base + (acc_it & 1u) * 2048u;
-            {
-                const int et = threadIdx.x - 10 * 32;  // 0..127
-                for (int j = et; j < ((p.BN + 31) & ~31); j += 128) {
-                    const int n = nt * p.BN + j;
-                    const bool in = j < p.BN && n < p.N;
-                    const float scv = in ? __ldg(p.scale + n) : 0.f, shv = in ? __ldg(p.shift + n) : 0.f;
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss + (uint32_t)j * 4u), "f"(scv) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss + 1024u + (uint32_t)j * 4u), "f"(shv) : "memory");
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-            }
-            mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
-            if (t == cluster_id && threadIdx.x == 10 * 32) K2Y_TRACE(8);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)p.BN;
-            // split-K partials of slice ks live at rows [ks * m_tiles * 128, ...) of the scratch tensor
-            const int m_base = (ks * p.m_tiles + mt) * BM + q * 32;
-            for (int c0 = 0; c0 < p.BN; c0 += 32, ++stg_it) {
-                const int ncols = (p.BN - c0) < 32 ? (p.BN - c0) : 32;  // 32 or 16
-                const int n0 = nt * p.BN + c0;
-                const uint32_t stg = stg_base + (stg_it & 1u) * 4096u;
-                uint32_t r[32];
-                const bool tr = p.trace && t == cluster_id && c0 == 32 && threadIdx.x == 10 * 32;
-                long long c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_4 = 0;
-                if (tr) c_0 = clock64();
-                tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-                if (ncols == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-                else {
-#pragma unroll
-                    for (int j = 16; j < 32; ++j) r[j] = 0u;
-                }
-                tmem_ld_wait();
-                if (tr) c_1 = clock64();
-                if (p.tma_store) {
-                    // scale/shift come from the shared-memory copy (zero beyond N, so no bounds checks); the activation is
-                    // specialised outside the element loop: leaky = max(v, slope*v), relu = max(v,0), relu6 = min(max(v,0),6)
-#define K2Y_EPI_LOOP(ACT_EXPR)                                                                                     \
-    _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                                             \
-        const float4 s4 = ld_shared_v4(ss + (uint32_t)(c0 + j) * 4u);                                               \
-        const float4 h4 = ld_shared_v4(ss + 1024u + (uint32_t)(c0 + j) * 4u);                                       \
-        float v;                                                                                                     \
-        v = fmaf(__uint_as_float(r[j]), s4.x, h4.x);     r[j] = __float_as_uint(ACT_EXPR);                           \
-        v = fmaf(__uint_as_float(r[j + 1]), s4.y, h4.y); r[j + 1] = __float_as_uint(ACT_EXPR);                       \
-        v = fmaf(__uint_as_float(r[j + 2]), s4.z, h4.z); r[j + 2] = __float_as_uint(ACT_EXPR);                       \
-        v = fmaf(__uint_as_float(r[j + 3]), s4.w, h4.w); r[j + 3] = __float_as_uint(ACT_EXPR);                       \
-    }
-                    if (p.act == ACT_LEAKY) {
-                        const float slope = p.act_slope;
-                        K2Y_EPI_LOOP(fmaxf(v, v * slope))
-                    } else if (p.act == ACT_RELU) {
-                        K2Y_EPI_LOOP(fmaxf(v, 0.f))
-                    } else if (p.act == ACT_RELU6) {
-                        K2Y_EPI_LOOP(fminf(fmaxf(v, 0.f), 6.f))
-                    } else {
-                        K2Y_EPI_LOOP(v)
-                    }
-#undef K2Y_EPI_LOOP
-                    if (tr) c_2 = clock64();
-                    // the staging buffer used two chunks ago must have been read by its TMA store
-                    if (lane == 0) tma_store_wait_read1();
-                    __syncwarp();
-                    if (tr) c_3 = clock64();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[j * 4], r[j * 4 + 1],
-                                     r[j * 4 + 2], r[j * 4 + 3]);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (tr) c_4 = clock64();
-                    if (lane == 0 && tile_ok && !(p.dbg & 1)) {
-                        tma_store_2d(&map_out, stg, n0, m_base);  // rows >= M and columns >= N are clipped by the TMA
-                        tma_store_commit();
-                    }
-                    if (tr) {
-                        long long *o = p.trace + (size_t)blockIdx.x * 64 + 48;
-                        o[0] = c_1 - c_0;
-                        o[1] = c_2 - c_1;
-                        o[2] = c_3 - c_2;
-                        o[3] = c_4 - c_3;
-                        o[4] = clock64() - c_4;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[j * 4], r[j * 4 + 1],
-                                     r[j * 4 + 2], r[j * 4 + 3]);
-                    __syncwarp();
-                    const int n = n0 + chunk * 4;
-                    const bool col_ok = (chunk * 4 < ncols) && (n < p.N);
-                    const bool full4 = n_vec && (n + 3 < p.N);
-                    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (col_ok) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (n + j < p.N) {
-                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc[j]) : "r"(ss + (uint32_t)(c0 + chunk * 4 + j) * 4u));
-                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sh[j]) : "r"(ss + 1024u + (uint32_t)(c0 + chunk * 4 + j) * 4u));
-                            }
-                    }
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = it * 4 + rsub;
-                        const int m = m_base + row;
-                        const float4 v = ld_shared_v4(stg + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
-                        if (col_ok && tile_ok && m < p.M && !(p.dbg & 1)) {
-                            float o[4];
-                            o[0] = act_bf(fmaf(v.x, sc[0], sh[0]), p.act_slope, p.act_clamp);
-                            o[1] = act_bf(fmaf(v.y, sc[1], sh[1]), p.act_slope, p.act_clamp);
-                            o[2] = act_bf(fmaf(v.z, sc[2], sh[2]), p.act_slope, p.act_clamp);
-                            o[3] = act_bf(fmaf(v.w, sc[3], sh[3]), p.act_slope, p.act_clamp);
-                            float *out = p.dst + (size_t)m * p.N + n;
-                            if (full4) {
-                                if (p.residual) {
-                                    const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + (size_t)m * p.N + n));
-                                    o[0] += rr.x, o[1] += rr.y, o[2] += rr.z, o[3] += rr.w;
-                                }
-                                *reinterpret_cast<float4 *>(out) = make_float4(o[0], o[1], o[2], o[3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (n + j < p.N) out[j] = o[j] + (p.residual ? __ldg(p.residual + (size_t)m * p.N + n + j) : 0.f);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->tmem_empty[a]));
-            if (t == cluster_id && threadIdx.x == 10 * 32) K2Y_TRACE(9);
-        }
-        if (p.tma_store && lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
-        if (threadIdx.x == 10 * 32) K2Y_TRACE(10);
+        epilogue(0, warp - 10);
     }
 
     tc_fence_before();
@@ -1090,6 +1107,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     const size_t smem = fixed + (size_t)stages * stage_bytes;
 
     const bool gather = !is_plain_1x1(a);
+    p.epi_groups = (!gather && p.BN > 32 && !getenv("K2Y_TC_ONE_EPI")) ? 2 : 1;
     CUtensorMap map_a, map_bhi, map_blo, map_out;
     memset(&map_a, 0, sizeof(map_a));
     memset(&map_out, 0, sizeof(map_out));
