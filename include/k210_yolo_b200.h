@@ -165,6 +165,16 @@ int k2y_region_workspace_bytes(const k2y_region_cfg *cfg, int batch, size_t *byt
 int k2y_region_run(const k2y_region_cfg *cfg, const float *in_dev, int batch, float *out_dev /* activations, may be NULL */,
                    float *probs_dev, float *boxes_dev, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Pre-processing: aspect-preserving letterbox of ONE uint8 HWC RGB image on the device
+ * (tools/utils.py:372-400: AffineTransform(scale, translation) + skimage warp order 1, zero fill, .astype('uint8')).
+ * inv_matrix_host: the first two rows of inv([[s,0,tx],[0,s,ty],[0,0,1]]) as 6 doubles (host memory) - what
+ * `aff.inverse` hands to warp.  dst_dev: [dst_h][dst_w][3] uint8, ready for k2y_net_bind_u8.  minmax_dev: 2 ints of
+ * device scratch (receives the source image's min and max, used by warp's output clipping).
+ * ---------------------------------------------------------------------------------------- */
+int k2y_letterbox_u8(const unsigned char *src_dev, int src_h, int src_w, const double *inv_matrix_host,
+                     unsigned char *dst_dev, int dst_h, int dst_w, int *minmax_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

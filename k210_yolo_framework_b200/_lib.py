@@ -85,6 +85,7 @@ _SIGNATURES = {
     "k2y_region_workspace_bytes": (c_int, [POINTER(RegionCfg), c_int, POINTER(c_size_t)]),
     "k2y_region_run": (c_int, [POINTER(RegionCfg), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
+    "k2y_letterbox_u8": (c_int, [c_void_p, c_int, c_int, POINTER(ctypes.c_double), c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 # include/region_layer.h (ABI-compatible firmware API)
 _REGION_ABI = ["region_layer_init", "region_layer_deinit", "region_layer_run", "region_layer_draw_boxes"]

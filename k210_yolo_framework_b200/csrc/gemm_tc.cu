@@ -272,6 +272,11 @@ struct TcParams {
     float act_slope, act_clamp;     // branch-free activation parameters
     int epi_groups;                 // 1, or 2: the idle gather warps form a second epilogue group (plain 1x1 convs)
     int tma_store;                  // 1: epilogue writes through a TMA store (N % 4 == 0, no residual)
+    // fused depthwise producer (gather variant, nkb == 1): A = act(BN(depthwise3x3(src0))) is computed by the gather warps
+    int dw;
+    const float *dw_w, *dw_scale, *dw_shift;  // [9][C0], [C0], [C0]
+    int dw_act;
+    float dw_alpha;
     int dbg;                        // bring-up switches (K2Y_TC_DBG): 1 skip stores, 2 skip tmem loads, 4 skip convert math
     long long *trace;               // optional [gridDim.x][16] globaltimer stamps (K2Y_TC_TRACE=1 via k2y_conv2d)
 };
@@ -294,7 +299,54 @@ struct __align__(8) Barriers {
 // dynamic smem besides the stage ring: alignment slack, barriers, epilogue staging (2 x 4 KB per epilogue warp)
 constexpr size_t FIXED_SMEM = 1024 + sizeof(Barriers) + 1024 + 4 * 8192 + 2 * 4096;  // + scale/shift copies of two epilogue groups
 
-template <bool GATHER>
+// Depthwise 3x3 + BN + activation for 4 horizontally adjacent outputs x 4 channels (fused producer of the 1x1 convs that
+// follow the early MobileNet depthwise layers).  The 3 x (3*STRIDE+3) input window is loaded once (clamped addresses, zero
+// for padding taps); tap order per output is (ky, kx) ascending like the stand-alone depthwise kernel.
+template <int STRIDE>
+__device__ __forceinline__ void dw_quad4(const TcParams &p, int b, int oy, int oxb, int c, float4 (&out)[4]) {
+    constexpr int NCOL = 3 * STRIDE + 3;
+    const int iy0 = oy * STRIDE - p.pad_t, ixb = oxb * STRIDE - p.pad_l;
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = iy0 + ky;
+        const bool row_ok = iy >= 0 && iy < p.H;
+        const float *rowp = p.src0 + (size_t)(b * p.H + min(max(iy, 0), p.H - 1)) * p.W * p.C0 + c;
+        float4 v[NCOL];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const int ix = ixb + j;
+            const bool ok = row_ok && ix >= 0 && ix < p.W;
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(rowp + (size_t)min(max(ix, 0), p.W - 1) * p.C0));
+            v[j] = ok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(p.dw_w + (ky * 3 + kx) * p.C0 + c));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 x = v[STRIDE * j + kx];
+                acc[j].x = fmaf(x.x, w.x, acc[j].x);
+                acc[j].y = fmaf(x.y, w.y, acc[j].y);
+                acc[j].z = fmaf(x.z, w.z, acc[j].z);
+                acc[j].w = fmaf(x.w, w.w, acc[j].w);
+            }
+        }
+    }
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.dw_scale + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.dw_shift + c));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        out[j].x = apply_act(fmaf(acc[j].x, sc.x, sh.x), p.dw_act, p.dw_alpha);
+        out[j].y = apply_act(fmaf(acc[j].y, sc.y, sh.y), p.dw_act, p.dw_alpha);
+        out[j].z = apply_act(fmaf(acc[j].z, sc.z, sh.z), p.dw_act, p.dw_alpha);
+        out[j].w = apply_act(fmaf(acc[j].w, sc.w, sh.w), p.dw_act, p.dw_alpha);
+    }
+}
+
+template <bool GATHER, bool DWFUSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
@@ -629,7 +681,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // so that 8 (tf32) or 16 (bf16) consecutive lanes copy one row's run: a cp.async warp instruction touches 4 or 2
         // full 128-byte lines instead of 32 different ones (the L1/LSU request rate was the limiter of the 3x3 convs).
         if (!GATHER && p.epi_groups == 2) epilogue(1, warp - 2);
-        if (GATHER) {
+        if (GATHER && DWFUSE) {
+            // ---- fused depthwise producer: the A tile is computed, not copied (one k-block per tile, K = C0 <= 64) ----
+            // work item = (channel quad, 4 consecutive GEMM rows = 4 horizontally adjacent output pixels; OW % 4 == 0);
+            // lanes run over the channel quads first, so a load instruction reads whole pixels' channel runs.
+            const int g = threadIdx.x - 64;
+            const int c4n = p.C0 >> 2;
+            for (int s2 = 0; s2 < p.stages; ++s2)  // columns >= C0 stay zero for the whole kernel (weights there are zero too)
+                for (uint32_t i = (uint32_t)g; i < a_bytes / 16u; i += 128u) st_shared_v4(stage_a_hi(s2) + i * 16u, 0u, 0u, 0u, 0u);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                const int mt = (t / p.n_tiles) * p.cluster + crank;
+                const long long tw0 = p.trace ? clock64() : 0;
+                mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                const long long tw1 = p.trace ? clock64() : 0;
+                if (mt < p.m_tiles) {
+                    const uint32_t stg_a = stage_a_hi(s);
+                    for (int it = g; it < c4n * (BM / 4); it += 128) {
+                        const int c = (it % c4n) * 4;
+                        const int seg = it / c4n;
+                        const int m0 = mt * BM + seg * 4;
+                        if (m0 >= p.M) continue;  // rows past the end keep older finite data; they are never stored
+                        const int oxb = m0 % p.OW;
+                        const int q = m0 / p.OW;
+                        const int oy = q % p.OH, b = q / p.OH;
+                        float4 o[4];
+                        if (p.stride == 1) dw_quad4<1>(p, b, oy, oxb, c, o);
+                        else dw_quad4<2>(p, b, oy, oxb, c, o);
+                        const uint32_t box = (uint32_t)(c >> 5) * A_TILE_BYTES;
+                        const uint32_t chunk = (uint32_t)((c & 31) >> 2);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t row = (uint32_t)(seg * 4 + j);
+                            st_shared_v4(stg_a + box + row * 128u + ((chunk ^ (row & 7u)) << 4), __float_as_uint(o[j].x),
+                                         __float_as_uint(o[j].y), __float_as_uint(o[j].z), __float_as_uint(o[j].w));
+                        }
+                    }
+                }
+                mbar_arrive(smem_u32(&bars->full_a[s]));
+                if (p.trace && g == 0) {  // producer timeline of this CTA: cycles waiting for a free stage / producing / tiles
+                    p.trace[(size_t)blockIdx.x * 64 + 53] += tw1 - tw0;
+                    p.trace[(size_t)blockIdx.x * 64 + 54] += clock64() - tw1;
+                    p.trace[(size_t)blockIdx.x * 64 + 55] += 1;
+                }
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        } else if (GATHER) {
             const int r = threadIdx.x - 64;  // GEMM row inside the tile, 0..127
             const int Cin = p.C0 + p.C1;
             const int wrow0 = (warp - 2) * 32;   // first tile row of this warp
@@ -970,9 +1072,11 @@ int tc_init() {
     K2Y_CUDA_CHECK(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     K2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)prop.sharedMemPerBlockOptin));
-    K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)prop.sharedMemPerBlockOptin));
+    K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)prop.sharedMemPerBlockOptin));
     g_max_smem = prop.sharedMemPerBlockOptin;
     g_num_sms = prop.multiProcessorCount;
@@ -1055,9 +1159,27 @@ bool tc_supported(const ConvArgs &a, const TcWeights &w) {
            (a.src1 == nullptr || (((uintptr_t)a.src1) & 15) == 0);
 }
 
-cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st) {
+// Depthwise 3x3 (+BN+act) followed by a plain 1x1 conv whose K fits one k-block: the depthwise result is produced straight
+// into the A stage of the tensor-core kernel (never written to HBM).  bf16x3 mode only (64 k per k-block).
+bool tc_dw_fusable(const DwArgs &dw, const ConvArgs &pw, const TcWeights &w, int math_mode) {
+    // opt-in (K2Y_DWPW_FUSION=1): correct, but with only four producer warps per SM the depthwise loads are latency-bound
+    // (6.6k / 18.8k cycles per tile on conv_dw_1 / conv_dw_2, see profiles/r01_dw_fusion.md) and the pair runs slower
+    // than the two separate launches.
+    const char *on = getenv("K2Y_DWPW_FUSION");
+    if (!on || on[0] != '1') return false;
+    if (math_mode != K2Y_MATH_TC_BF16X3 || !is_plain_1x1(pw) || !tc_supported(pw, w)) return false;
+    if (pw.src0 != dw.dst || pw.C0 != dw.C || pw.C1 != 0 || pw.OH != dw.OH || pw.OW != dw.OW || pw.residual) return false;
+    if (dw.C > 64 || (dw.C & 3) || (dw.OW & 3) || (pw.N & 3) || (dw.stride != 1 && dw.stride != 2)) return false;
+    return (((uintptr_t)dw.src) & 15) == 0 && (((uintptr_t)pw.dst) & 15) == 0;
+}
+
+cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st, const DwArgs *dw) {
     if (g_num_sms == 0) return cudaErrorNotReady;
     TcParams p;
+    p.dw = 0;
+    p.dw_w = p.dw_scale = p.dw_shift = nullptr;
+    p.dw_act = ACT_NONE;
+    p.dw_alpha = 0.f;
     p.src0 = a.src0;
     p.src1 = a.src1;
     p.H = a.H;
@@ -1083,13 +1205,27 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.M = a.B * a.OH * a.OW;
     p.N = a.N;
     p.K = w.K;
+    if (dw) {  // fused depthwise producer: the gather warps read the depthwise INPUT
+        p.dw = 1;
+        p.src0 = dw->src;
+        p.H = dw->H;
+        p.W = dw->W;
+        p.stride = dw->stride;
+        p.pad_t = dw->pad_t;
+        p.pad_l = dw->pad_l;
+        p.dw_w = dw->w;
+        p.dw_scale = dw->scale;
+        p.dw_shift = dw->shift;
+        p.dw_act = dw->act;
+        p.dw_alpha = dw->alpha;
+    }
     math_mode = effective_mode(a, math_mode);
     p.bf16 = (math_mode == K2Y_MATH_TC_BF16X3) ? 1 : 0;
     p.three_x = (math_mode == K2Y_MATH_TC_TF32) ? 0 : 1;
     p.a_boxes = p.bf16 ? 2 : 1;
     p.nkb = p.bf16 ? w.Kpad64 / 64 : w.Kpad / BK;
     p.cluster = pick_cluster(p.M, p.nkb);
-    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a), p.cluster, &p.BN, &p.k_splits);
+    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a) || dw, p.cluster, &p.BN, &p.k_splits);
     p.n_tiles = (w.Npad + p.BN - 1) / p.BN;
     p.m_tiles = (p.M + BM - 1) / BM;
     p.kb_per_split = (p.nkb + p.k_splits - 1) / p.k_splits;
@@ -1106,7 +1242,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.tmem_cols = cols;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
 
-    const bool gather = !is_plain_1x1(a);
+    const bool gather = !is_plain_1x1(a) || dw != nullptr;
     p.epi_groups = (!gather && p.BN > 32 && !getenv("K2Y_TC_ONE_EPI")) ? 2 : 1;
     CUtensorMap map_a, map_bhi, map_blo, map_out;
     memset(&map_a, 0, sizeof(map_a));
@@ -1165,8 +1301,9 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, map_a, map_bhi, map_blo, map_out, p)
-                                : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, map_a, map_bhi, map_blo, map_out, p);
+        cudaError_t le = dw       ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_bhi, map_blo, map_out, p)
+                         : gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_bhi, map_blo, map_out, p)
+                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, map_a, map_bhi, map_blo, map_out, p);
         if (le != cudaSuccess) return le;
     }
     if (d_trace) {
@@ -1187,6 +1324,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         // per-k-block pipeline of CTA 0's first tile: tma issue / landed (converter sees it) / converted / mma issued / slot free again
         fprintf(stderr, "[tc-trace] epilogue chunk cycles: tmem_ld+wait=%lld math=%lld wait_read=%lld sts+fence=%lld tma_issue=%lld\n", h[48],
                 h[49], h[50], h[51], h[52]);
+        if (p.dw) fprintf(stderr, "[tc-trace] dw producer (cta 0): wait_empty=%lld produce=%lld cycles over %lld tiles\n", h[53], h[54], h[55]);
         fprintf(stderr, "[tc-trace] kb: tma_issue landed converted mma_issued\n");
         for (int kb = 0; kb < 8; ++kb) {
             fprintf(stderr, "[tc-trace]  %d:", kb);

@@ -18,6 +18,8 @@ int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N);  // kernel_kn: 
 void tc_free(TcWeights &w);
 bool tc_supported(const ConvArgs &a, const TcWeights &w);
 int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode);  // kernels one launch_conv_tc issues
-cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st);
+// dw != nullptr: `a` is the plain 1x1 conv that follows the depthwise layer *dw; both run in one launch (tc_dw_fusable)
+cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st, const DwArgs *dw = nullptr);
+bool tc_dw_fusable(const DwArgs &dw, const ConvArgs &pw, const TcWeights &w, int math_mode);
 
 }  // namespace k2y

@@ -56,6 +56,7 @@ struct Layer {
     // device
     float *d_w = nullptr, *d_scale = nullptr, *d_shift = nullptr;
     TcWeights tc;  // tensor-core packing (gemm_tc.cu)
+    int fused = 0;  // last issue_layers(): 1 = this depthwise ran fused with the next 1x1 conv, 2 = this conv ran inside the previous launch
 };
 
 }  // namespace
@@ -397,35 +398,43 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
         }
         n->launches += 1;
     }
-    for (Layer &L : n->layers) {
+    auto conv_args = [&](const Layer &L) {
+        const Tensor &s0 = n->tensors[L.src0];
+        const Tensor &d = n->tensors[L.dst];
+        ConvArgs a;
+        a.src0 = tensor_ptr(n, L.src0);
+        a.src1 = L.src1 >= 0 ? tensor_ptr(n, L.src1) : nullptr;
+        a.residual = L.res >= 0 ? tensor_ptr(n, L.res) : nullptr;
+        a.dst = const_cast<float *>(tensor_ptr(n, L.dst));
+        a.w = L.d_w;
+        a.scale = L.d_scale;
+        a.shift = L.d_shift;
+        a.B = batch;
+        a.H = L.up0 ? s0.h * 2 : s0.h;
+        a.W = L.up0 ? s0.w * 2 : s0.w;
+        a.C0 = s0.c;
+        a.C1 = L.src1 >= 0 ? n->tensors[L.src1].c : 0;
+        a.up0 = L.up0 ? 1 : 0;
+        a.OH = d.h;
+        a.OW = d.w;
+        a.N = L.cout;
+        a.kh = L.kh;
+        a.kw = L.kw;
+        a.stride = L.stride;
+        a.pad_t = L.pad_t;
+        a.pad_l = L.pad_l;
+        a.act = L.act;
+        a.alpha = L.alpha;
+        return a;
+    };
+    for (size_t idx = 0; idx < n->layers.size(); ++idx) {
+        Layer &L = n->layers[idx];
+        L.fused = 0;
         const Tensor &s0 = n->tensors[L.src0];
         const Tensor &d = n->tensors[L.dst];
         cudaError_t e = cudaSuccess;
         if (L.kind == L_CONV) {
-            ConvArgs a;
-            a.src0 = tensor_ptr(n, L.src0);
-            a.src1 = L.src1 >= 0 ? tensor_ptr(n, L.src1) : nullptr;
-            a.residual = L.res >= 0 ? tensor_ptr(n, L.res) : nullptr;
-            a.dst = const_cast<float *>(tensor_ptr(n, L.dst));
-            a.w = L.d_w;
-            a.scale = L.d_scale;
-            a.shift = L.d_shift;
-            a.B = batch;
-            a.H = L.up0 ? s0.h * 2 : s0.h;
-            a.W = L.up0 ? s0.w * 2 : s0.w;
-            a.C0 = s0.c;
-            a.C1 = L.src1 >= 0 ? n->tensors[L.src1].c : 0;
-            a.up0 = L.up0 ? 1 : 0;
-            a.OH = d.h;
-            a.OW = d.w;
-            a.N = L.cout;
-            a.kh = L.kh;
-            a.kw = L.kw;
-            a.stride = L.stride;
-            a.pad_t = L.pad_t;
-            a.pad_l = L.pad_l;
-            a.act = L.act;
-            a.alpha = L.alpha;
+            ConvArgs a = conv_args(L);
             if (n->x_u8 && n->tensors[L.src0].is_input) {
                 if (!(L.kh == 3 && s0.c == 3 && L.src1 < 0 && (L.cout == 16 || L.cout == 24 || L.cout == 32))) {
                     set_error("uint8 input is only supported in front of a 3x3, Cin=3 first convolution");
@@ -459,8 +468,32 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
             a.pad_l = L.pad_l;
             a.act = L.act;
             a.alpha = L.alpha;
-            e = launch_dwconv(a, st);
-            n->launches += 1;
+            // optional (K2Y_DWPW_FUSION=1): depthwise + the following 1x1 conv as one tensor-core launch, the depthwise output
+            // goes straight into the GEMM's A stage (skipped when every layer output must be readable)
+            bool fused = false;
+            if (!n->keep_all && n->math != K2Y_MATH_FP32_SIMT && idx + 1 < n->layers.size()) {
+                const Layer &P = n->layers[idx + 1];
+                const Tensor &dt = n->tensors[L.dst];
+                if (P.kind == L_CONV && P.src0 == L.dst && dt.last_use == (int)idx + 1 && dt.out_index < 0) {
+                    const ConvArgs pa = conv_args(P);
+                    if (tc_dw_fusable(a, pa, P.tc, n->math)) {
+                        e = launch_conv_tc(pa, P.tc, n->math, st, &a);
+                        n->launches += 1;
+                        fused = true;
+                        if (e == cudaSuccess) {
+                            ++li;
+                            if (ev) cudaEventRecord(ev[li], st);
+                            L.fused = 1;
+                            n->layers[idx + 1].fused = 2;
+                            ++idx;  // the pointwise layer is done
+                        }
+                    }
+                }
+            }
+            if (!fused) {
+                e = launch_dwconv(a, st);
+                n->launches += 1;
+            }
         } else {
             PoolArgs a;
             a.src = tensor_ptr(n, L.src0);
@@ -934,8 +967,20 @@ extern "C" int k2y_net_launch_info(const k2y_net *net, int i, char *name, int na
     double macs = 0;
     if (L.kind == L_CONV) macs = out_elems * L.kh * L.kw * L.cin;
     else if (L.kind == L_DW) macs = out_elems * 9;
+    double bytes = 4.0 * (in_elems + out_elems);  // algorithmic: activations read once + written once
+    if (L.fused == 1) {  // depthwise + next 1x1 in one launch: reads the depthwise input, writes the pointwise output
+        const Layer &P = net->layers[i + 1];
+        const Tensor &pd = net->tensors[P.dst];
+        const double p_out = (double)pd.h * pd.w * pd.c;
+        if (name && name_len > 0) snprintf(name, name_len, "%s+%s", L.name.c_str(), P.name.c_str());
+        macs += p_out * P.cin;
+        bytes = 4.0 * (in_elems + p_out);
+    } else if (L.fused == 2) {  // ran inside the previous launch
+        macs = 0;
+        bytes = 0;
+    }
     if (flops_per_image) *flops_per_image = 2.0 * macs;
-    if (bytes_per_image) *bytes_per_image = 4.0 * (in_elems + out_elems);  // algorithmic: activations read once + written once
+    if (bytes_per_image) *bytes_per_image = bytes;
     return K2Y_OK;
 }
 

@@ -39,28 +39,26 @@ class Helper(object):
     def _process_img(self, img: np.ndarray, true_box=None, is_training: bool = False, is_resize: bool = True):
         """tools/utils.py:357-406, inference branch: letterbox to in_hw[0] then ``img / np.max(img)``.
 
-        The affine parameters follow the reference exactly (scale = min(in_wh/img_wh), translation =
-        ((in_wh - img_wh*scale)/2).astype(int)).  The resampling itself is skimage 0.15's ``warp``
-        (order-1, constant 0 fill; third-party, not available offline); it is restated here with
-        cv2.warpAffine bilinear — identical when the image already has the network size (identity warp),
-        approximate otherwise (SURVEY.md §8c "secondary, approximate known answer").
+        The resampling runs on the GPU (``preprocess.letterbox_device`` -> k2y_letterbox_u8): the affine parameters follow the
+        reference exactly (scale = min(in_wh/img_wh), translation = ((in_wh - img_wh*scale)/2).astype(int)) and the
+        interpolation restates skimage 0.15's ``warp`` (order 1, zero fill, clip, uint8 truncation; third-party, not
+        available offline — oracle/preprocess_ref.py).  Exact for an image that already has the network size.
+        Returns the reference's value: a float64 HxWx3 array in [0, 1] on the host.
         """
         if is_training:
             raise NotImplementedError("augmentation is out of scope for the inference path")
         if is_resize:
-            img_wh = np.array([img.shape[1], img.shape[0]])
-            in_wh = self.in_hw[0][::-1]
-            scale = in_wh / img_wh
-            scale[:] = np.min(scale)
-            translation = ((in_wh - img_wh * scale) / 2).astype(int)
-            if not (scale[0] == 1.0 and translation[0] == 0 and translation[1] == 0
-                    and img.shape[0] == self.in_hw[0][0] and img.shape[1] == self.in_hw[0][1]):
-                import cv2
-                m = np.array([[scale[0], 0, translation[0]], [0, scale[1], translation[1]]], np.float64)
-                img = cv2.warpAffine(img, m, (int(in_wh[0]), int(in_wh[1])), flags=cv2.INTER_LINEAR,
-                                     borderMode=cv2.BORDER_CONSTANT, borderValue=0).astype("uint8")
+            img = self.letterbox_device(img).cpu().numpy()
         img = img / np.max(img)
         return img, true_box
+
+    def letterbox_device(self, img: np.ndarray):
+        """uint8 HWC host image -> CUDA uint8 [in_h, in_w, 3]: the input of the network's uint8 front end
+        (``predict_device_u8``), which applies ``img / np.max(img)`` on the GPU."""
+        import torch
+        from .preprocess import letterbox_device
+        x = torch.from_numpy(np.ascontiguousarray(img[..., :3], dtype=np.uint8)).cuda()
+        return letterbox_device(x, self.in_hw[0])
 
 
 _COLORMAP = [

@@ -321,6 +321,10 @@ class YoloModel:
     def predict_device(self, x: torch.Tensor) -> List[torch.Tensor]:
         return [self._shape(o) for o in self.engine.predict_device(x)]
 
+    def predict_device_u8(self, x_u8: torch.Tensor) -> List[torch.Tensor]:
+        """CUDA uint8 [N,H,W,3] letterboxed RGB in; ``img / np.max(img)`` (tools/utils.py:405) runs on the GPU."""
+        return [self._shape(o) for o in self.engine.predict_device_u8(x_u8)]
+
     @property
     def output_shapes(self):
         a, c = self.engine.anchor_num, self.engine.class_num

@@ -38,10 +38,10 @@ def detect(ckpt_weights, image_size, output_size, model_def, class_num, depth_mu
     print(INFO, f' Load CKPT {str(ckpt_weights)}')
     orig_img = h._read_img(str(test_image))
     image_shape = orig_img.shape[0:2]
-    img, _ = h._process_img(orig_img, true_box=None, is_training=False, is_resize=True)
-
-    x = torch.from_numpy(np.ascontiguousarray(img[None], dtype=np.float32)).cuda()
-    y_pred = yolo_model_warpper.predict_device(x)
+    # reference: h._process_img(orig_img, None, False, True) on the CPU, then predict (:84-88).  Here the decoded uint8
+    # image goes to the GPU as is: letterbox kernel -> uint8 front end (img / np.max(img) fused into the first conv)
+    x_u8 = h.letterbox_device(orig_img)
+    y_pred = yolo_model_warpper.predict_device_u8(x_u8[None])
 
     grid = [tuple(int(v) for v in t.shape[1:3]) for t in y_pred]
     if [tuple(int(v) for v in hw) for hw in h.out_hw] != grid:

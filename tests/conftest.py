@@ -31,6 +31,11 @@ def dog_u8():
 
 
 @pytest.fixture(scope="session")
+def people_u8():
+    return np.load(os.path.join(GOLDEN, "people_u8.npy"))
+
+
+@pytest.fixture(scope="session")
 def dog_heads():
     z = np.load(os.path.join(GOLDEN, "dog_heads.npz"))
     return {k: z[k] for k in z.files}

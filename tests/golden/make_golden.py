@@ -11,7 +11,12 @@ Outputs of the oracle / compiled reference on them:
   dog_heads_f32.npz     oracle fp32 head tensors (TF-CPU stand-in) and fp64 ground truth
   dog_golden.json       KERAS-dialect detections (obj 0.7, iou 0.5) + REGION_C draw list from the
                         *compiled reference* region_layer.c (thr 0.6, nms 0.3 — main.c:280-287)
+  people_golden.json    data/people.jpg (374x499) through the restated letterbox (oracle/preprocess_ref.py; skimage is
+                        not available offline -> "parity unpinned" for the resampling) + oracle network + KERAS decode:
+                        sha256 / sample pixels of the letterboxed uint8 input and the five class-14 detections that
+                        asset/people_res.jpg shows.  `--people-only` regenerates it from the committed fixtures alone.
 """
+import hashlib
 import json
 import os
 import sys
@@ -59,5 +64,30 @@ def main():
     print(json.dumps(gold, indent=1))
 
 
+def people_golden():
+    from k210_yolo_framework_b200.yolonet import load_npz_weights
+    from oracle import preprocess_ref
+    w = load_npz_weights(f"{OUT}/yolo_mobilev1_075_voc_weights.npz")
+    anchors = np.load(f"{OUT}/voc_anchor.npy")
+    img = np.load(f"{OUT}/people_u8.npy")
+    scale, tr, inv = preprocess_ref.letterbox_params(img.shape[:2], (224, 320))
+    lb = preprocess_ref.letterbox(img, (224, 320))
+    x = (lb / np.max(lb)).astype(np.float32)[None]
+    heads32 = keras_ref.forward("yolo_mobilev1", w, x, alpha=0.75)
+    h = decode_ref.HelperRef(anchors, [224, 320], [7, 10, 14, 20], 20)
+    yp = [hd[0].reshape(hd.shape[1], hd.shape[2], 3, 25) for hd in heads32]
+    det = decode_ref.detect_image(yp, h, [224, 320], img.shape[:2], 0.7, 0.5)
+    samples = [[r, c] + [int(v) for v in lb[r, c]] for r, c in [(0, 10), (100, 150), (223, 309), (57, 200), (180, 11)]]
+    gold = {"image_hw": list(img.shape[:2]), "in_hw": [224, 320], "scale": float(scale[0]), "translation": [int(t) for t in tr],
+            "letterbox_sha256": hashlib.sha256(lb.tobytes()).hexdigest(), "letterbox_samples_r_c_rgb": samples,
+            "obj_thresh": 0.7, "iou_thresh": 0.5,
+            "detections": [[int(d[0]), int(d[1])] + [float(v) for v in d[2:]] for d in det]}
+    with open(f"{OUT}/people_golden.json", "w") as fh:
+        json.dump(gold, fh, indent=1)
+    print(json.dumps(gold, indent=1))
+
+
 if __name__ == "__main__":
-    main()
+    if "--people-only" not in sys.argv:
+        main()
+    people_golden()

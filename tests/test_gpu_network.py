@@ -102,6 +102,35 @@ def test_device_api_graph_replay_and_batching():
     assert m.engine.launches_per_run() >= 32   # + split-K reducers
 
 
+def test_fused_depthwise_pointwise_blocks(monkeypatch):
+    """Opt-in schedule (K2Y_DWPW_FUSION=1): the first two MobileNet blocks run depthwise+pointwise as one tensor-core
+    launch (the gather warps compute the depthwise tile into the GEMM's A stage); same heads as the default schedule."""
+    m, _ = yolonet.yolo_mobilev1([224, 320, 3], 3, 20, alpha=0.75, max_batch=3)
+    weights = random_weights(m.engine.expected_variables(), seed=9, detection_rich=True)
+    m.set_weights_dict(weights)
+    m.engine.set_use_graph(False)
+    x = torch.rand((3, 224, 320, 3), device="cuda")
+    plain = [t.clone() for t in m.predict_device(x)]
+    n_plain = m.engine.launches_per_run()
+    monkeypatch.setenv("K2Y_DWPW_FUSION", "1")
+    fused = [t.clone() for t in m.predict_device(x)]
+    assert m.engine.launches_per_run() == n_plain - 2
+    names = [p["name"] for p in m.engine.profile(3)]
+    assert "conv_dw_1+conv_pw_1" in names and "conv_dw_2+conv_pw_2" in names
+    for p, q in zip(fused, plain):
+        assert torch.allclose(p, q, atol=3e-4, rtol=1e-4), float((p - q).abs().max())
+    # against the oracle, on extents where the last GEMM tile is partial
+    m2, _ = yolonet.yolo_mobilev1([96, 160, 3], 3, 20, alpha=0.5, max_batch=2)
+    w2 = random_weights(m2.engine.expected_variables(), seed=10, detection_rich=True)
+    m2.set_weights_dict(w2)
+    x2 = np.random.default_rng(3).random((2, 96, 160, 3), dtype=np.float32)
+    got = m2.predict(x2)
+    assert any("+" in p["name"] for p in m2.engine.profile(2))
+    ref = keras_ref.forward("yolo_mobilev1", w2, x2.astype(np.float64), alpha=0.5, dtype=torch.float64)
+    for g, r in zip(got, ref):
+        assert _maxerr(g, r) / max(1.0, float(np.abs(r).max())) < LAYER_TOL[_lib.MATH_TC_BF16X3]
+
+
 def test_errors():
     m, _ = yolonet.yolo_mobilev1([224, 320, 3], 3, 20, alpha=0.75, max_batch=2)
     with pytest.raises(_lib.K2YError):
