@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 
 #include "../../include/k210_yolo_b200.h"
@@ -67,6 +68,31 @@ cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st);
 cudaError_t launch_dwconv(const DwArgs &a, cudaStream_t st);
 cudaError_t launch_maxpool(const PoolArgs &a, cudaStream_t st);
 cudaError_t launch_image_max_u8(const unsigned char *x, int batch, size_t bytes_per_image, int *max_out, cudaStream_t st);
+
+// Programmatic dependent launch: every kernel of a step is launched with programmaticStreamSerializationAllowed, calls
+// pdl_trigger() first thing (the next kernel's CTAs may be scheduled as soon as this grid's CTAs have all started and
+// SM resources free up) and pdl_wait() before it touches anything a predecessor wrote or may still read (returns once
+// the preceding grid has completed and flushed).  Hides the launch gap and the next kernel's prologue behind the tail of
+// the current one; K2Y_NO_PDL=1 falls back to plain stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
     if (act == ACT_LEAKY) return v >= 0.f ? v : v * alpha;

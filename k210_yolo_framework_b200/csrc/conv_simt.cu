@@ -6,9 +6,14 @@
 // Replaces the TF ops the reference reaches through keras predict (keras_inference.py:88):
 // Conv2D / DepthwiseConv2dNative / FusedBatchNorm / LeakyRelu / Relu(6) / ResizeNearestNeighbor /
 // ConcatV2 / MaxPool / Add, as composed by models/yolonet.py and models/keras_mobilenet*.py.
+#include <cstdlib>
+
 #include "common.h"
 
 namespace k2y {
+
+bool pdl_enabled() { return getenv("K2Y_NO_PDL") == nullptr; }
+
 
 namespace {
 
@@ -29,6 +34,8 @@ __device__ __forceinline__ const float *src_ptr(const ConvArgs &a, int b, int iy
 
 template <int TM, bool VEC>
 __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const ConvArgs a) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int BM = 16 * TM;
     constexpr int A_PER_T = VEC ? (BM / 64) : (BM / 16);  // float4s or scalars of A per thread per k-tile
     __shared__ __align__(16) float As[BK_T][BM + 4];
@@ -206,6 +213,8 @@ __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const ConvArgs a) 
 // ((TY-1)*S+3)*((TX-1)*S+3) / (TY*TX)  (3x for stride 1 with 2x4 outputs).  grid = (ceil(XT*C4 / 128), B*ceil(OH/TY)).
 template <int STRIDE, int TX, int TY>
 __global__ void __launch_bounds__(128) dwconv3x3_kernel(const DwArgs a) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCOL = (TX - 1) * STRIDE + 3;
     constexpr int NROW = (TY - 1) * STRIDE + 3;
     const int c4n = a.C >> 2;
@@ -283,6 +292,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const DwArgs a) {
 // output channels; the 27 x COUT weights sit in shared memory and are read as warp-wide broadcasts.
 template <int COUT, bool U8>
 __global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a) {
+    pdl_trigger();
     __shared__ __align__(16) float ws[27 * COUT];
     __shared__ __align__(16) float sc[COUT], sh[COUT];
     __shared__ float lut[U8 ? 256 : 1];  // u8 -> u8 / max(image) with the IEEE division the reference's float32 cast implies
@@ -293,6 +303,7 @@ __global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a) {
     }
     const int row = blockIdx.y;
     const int oy = row % a.OH, b = row / a.OH;
+    pdl_wait();  // weights above are constants; the image maximum / input / output below belong to the stream order
     if (U8) {
         const float mx = (float)a.img_max[b];
         for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = __fdiv_rn((float)v, mx);
@@ -365,6 +376,8 @@ __global__ void __launch_bounds__(256) image_max_u8_kernel(const unsigned char *
 }
 
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const PoolArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int c4n = a.C >> 2;
     const size_t total = (size_t)a.B * a.OH * a.OW * c4n;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,13 +415,13 @@ cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
     if (a.kh == 3 && a.kw == 3 && a.C0 == 3 && a.C1 == 0 && !a.up0 && !a.residual && (a.N == 16 || a.N == 24 || a.N == 32)) {
         dim3 grid((a.OW + 127) / 128, a.B * a.OH);
         if (a.src_u8) {
-            if (a.N == 16) first_conv3x3_kernel<16, true><<<grid, 128, 0, st>>>(a);
-            else if (a.N == 24) first_conv3x3_kernel<24, true><<<grid, 128, 0, st>>>(a);
-            else first_conv3x3_kernel<32, true><<<grid, 128, 0, st>>>(a);
+            if (a.N == 16) launch_k(first_conv3x3_kernel<16, true>, grid, dim3(128), 0, st, a);
+            else if (a.N == 24) launch_k(first_conv3x3_kernel<24, true>, grid, dim3(128), 0, st, a);
+            else launch_k(first_conv3x3_kernel<32, true>, grid, dim3(128), 0, st, a);
         } else {
-            if (a.N == 16) first_conv3x3_kernel<16, false><<<grid, 128, 0, st>>>(a);
-            else if (a.N == 24) first_conv3x3_kernel<24, false><<<grid, 128, 0, st>>>(a);
-            else first_conv3x3_kernel<32, false><<<grid, 128, 0, st>>>(a);
+            if (a.N == 16) launch_k(first_conv3x3_kernel<16, false>, grid, dim3(128), 0, st, a);
+            else if (a.N == 24) launch_k(first_conv3x3_kernel<24, false>, grid, dim3(128), 0, st, a);
+            else launch_k(first_conv3x3_kernel<32, false>, grid, dim3(128), 0, st, a);
         }
         return cudaGetLastError();
     }
@@ -419,15 +432,15 @@ cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
     if (small) {
         dim3 grid((M + 63) / 64, gy);
         if (vec)
-            conv_igemm_simt_kernel<4, true><<<grid, 256, 0, st>>>(a);
+            launch_k(conv_igemm_simt_kernel<4, true>, grid, dim3(256), 0, st, a);
         else
-            conv_igemm_simt_kernel<4, false><<<grid, 256, 0, st>>>(a);
+            launch_k(conv_igemm_simt_kernel<4, false>, grid, dim3(256), 0, st, a);
     } else {
         dim3 grid((M + 127) / 128, gy);
         if (vec)
-            conv_igemm_simt_kernel<8, true><<<grid, 256, 0, st>>>(a);
+            launch_k(conv_igemm_simt_kernel<8, true>, grid, dim3(256), 0, st, a);
         else
-            conv_igemm_simt_kernel<8, false><<<grid, 256, 0, st>>>(a);
+            launch_k(conv_igemm_simt_kernel<8, false>, grid, dim3(256), 0, st, a);
     }
     return cudaGetLastError();
 }
@@ -437,10 +450,10 @@ cudaError_t launch_dwconv(const DwArgs &a, cudaStream_t st) {
     const int per_row = ((a.OW + TX - 1) / TX) * (a.C / 4);
     if (a.stride == 1) {  // two output rows per thread (measured: 31 -> 27 us on conv_dw_1); stride 2 is faster with one
         dim3 grid((per_row + 127) / 128, a.B * ((a.OH + 1) / 2));
-        dwconv3x3_kernel<1, TX, 2><<<grid, 128, 0, st>>>(a);
+        launch_k(dwconv3x3_kernel<1, TX, 2>, grid, dim3(128), 0, st, a);
     } else {
         dim3 grid((per_row + 127) / 128, a.B * a.OH);
-        dwconv3x3_kernel<2, TX, 1><<<grid, 128, 0, st>>>(a);
+        launch_k(dwconv3x3_kernel<2, TX, 1>, grid, dim3(128), 0, st, a);
     }
     return cudaGetLastError();
 }
@@ -449,13 +462,13 @@ cudaError_t launch_image_max_u8(const unsigned char *x, int batch, size_t bytes_
     cudaError_t e = cudaMemsetAsync(max_out, 0, (size_t)batch * sizeof(int), st);
     if (e != cudaSuccess) return e;
     dim3 grid(64, batch);
-    image_max_u8_kernel<<<grid, 256, 0, st>>>(x, bytes_per_image, max_out);
+    image_max_u8_kernel<<<grid, 256, 0, st>>>(x, bytes_per_image, max_out);  // follows a memset: plain stream order
     return cudaGetLastError();
 }
 
 cudaError_t launch_maxpool(const PoolArgs &a, cudaStream_t st) {
     const size_t total = (size_t)a.B * a.OH * a.OW * (a.C / 4);
-    maxpool2x2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    launch_k(maxpool2x2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a);
     return cudaGetLastError();
 }
 

@@ -282,6 +282,8 @@ __device__ __forceinline__ float4 decode_box(const KerasParams &p, const BoxXfor
 // (score = sigmoid(cls) * sigmoid(conf)), compacts the candidates in index order into sort keys, sorts them, decodes
 // the candidate boxes 32 at a time (one per lane) and runs the greedy suppression with shuffles.
 __global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const KerasParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned long long smem_keys[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
@@ -649,7 +651,7 @@ extern "C" int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *h
         K2Y_CUDA_CHECK(cudaMalloc(&p.trace, (size_t)batch * p.C * 4 * sizeof(long long)));
         K2Y_CUDA_CHECK(cudaMemset(p.trace, 0, (size_t)batch * p.C * 4 * sizeof(long long)));
     }
-    detect_keras_kernel<<<grid, DET_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    launch_k(detect_keras_kernel, grid, dim3(DET_WARPS * 32), smem, (cudaStream_t)stream, p);
     K2Y_CUDA_CHECK(cudaGetLastError());
     if (p.trace) {
         K2Y_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));

@@ -365,6 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     Barriers *bars = reinterpret_cast<Barriers *>(smem_gen + (size_t)p.stages * stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     const bool use_conv = p.three_x || GATHER;
     const int crank = p.cluster == 2 ? (int)cluster_ctarank() : 0;
     const int cluster_id = (int)blockIdx.x / p.cluster, num_clusters = (int)gridDim.x / p.cluster;
@@ -394,6 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_slot;
     if (threadIdx.x == 0) K2Y_TRACE(1);
+    pdl_wait();  // barriers / TMEM / descriptor prefetch above overlap the previous kernel's tail; activations do not
 
     const int mp_tiles = (p.m_tiles + p.cluster - 1) / p.cluster;
     const int num_tiles = mp_tiles * p.n_tiles * p.k_splits;   // work items per cluster sequence
@@ -895,6 +897,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
                                                             const float *__restrict__ residual, const float *__restrict__ scale,
                                                             const float *__restrict__ shift, int M, int N, int splits,
                                                             size_t split_stride, float slope, float clamp) {
+    pdl_trigger();
+    pdl_wait();
     const int n4 = N >> 2;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)M * n4) return;
@@ -1022,7 +1026,7 @@ void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int 
         int stages = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage);
         if (three_x) stages = stages < (512 - 2 * bn) / 64 ? stages : (512 - 2 * bn) / 64;  // A planes live in TMEM: 64 columns / stage
         if (stages > MAX_STAGES) stages = MAX_STAGES;
-        if (stages < 3 && bn > 16 && !force_bn) continue;
+        if (stages < 3 && bn > 16 && !force_bn && !bf16) continue;  // tf32 modes: not re-measured with 2-stage tiles
         if (stages < 2) continue;
         const int n_tiles = (n16 + bn - 1) / bn;
         if (n_tiles > 1 && (bn % 32) != 0) continue;
@@ -1038,7 +1042,10 @@ void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int 
         const double smem_bytes = (double)a_bytes + bn * 128.0 * (three_x ? 2 : 1) + (three_x ? (double)a_bytes : 4.0 * 4096.0) +
                                   passes * 4.0 * bn * 32.0;
         const double smem_t = smem_bytes / 128.0;
-        const double lat = (gather ? 5000.0 : 3000.0) / stages;
+        // measured per-k-block times (bf16x3, profiles/r01_tile_model.md): gather 64/3 stages 1310 cycles, 96/3 1370, 128/2 1615,
+        // 192/2 1840; plain 96/3 1000, 192/2 1900  ->  round trip ~ L0 + 5.5 * bn, shared by the stages in flight
+        const double lat = bf16 ? ((gather ? (stages >= 3 ? 3300.0 : 2600.0) : 2500.0) + 5.5 * bn) / stages
+                                : (gather ? 5000.0 : 3000.0) / stages;
         double kbt = mma > lat ? mma : lat;
         if (conv > kbt) kbt = conv;
         if (smem_t > kbt) kbt = smem_t;
@@ -1141,7 +1148,9 @@ void tc_free(TcWeights &w) {
 static bool is_plain_1x1(const ConvArgs &a);
 static int effective_mode(const ConvArgs &a, int math_mode) {
     if (math_mode != K2Y_MATH_TC_BF16X3) return math_mode;
-    if (is_plain_1x1(a)) return math_mode;
+    // K <= 32 fits one 32-wide tf32 k-block: half the A bytes staged and converted per tile of the 64-wide bf16 k-block
+    // (conv_pw_1 of yolo_mobilev1-0.75: 56 us as 3xTF32, 64 us as bf16x3); same error class
+    if (is_plain_1x1(a)) return (a.C0 + a.C1 <= 32) ? K2Y_MATH_TC_3XTF32 : math_mode;
     const int Cin = a.C0 + a.C1;
     return ((Cin % 64) == 0 && (a.C0 % 64) == 0) ? math_mode : K2Y_MATH_TC_3XTF32;
 }
@@ -1294,13 +1303,15 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)p.cluster;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = (pdl_enabled() && !d_trace) ? 2 : 1;
         cudaError_t le = dw       ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_bhi, map_blo, map_out, p)
                          : gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_bhi, map_blo, map_out, p)
                                   : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, map_a, map_bhi, map_blo, map_out, p);
@@ -1338,8 +1349,8 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         const float slope = a.act == ACT_NONE ? 1.f : (a.act == ACT_LEAKY ? a.alpha : 0.f);
         const float clamp = a.act == ACT_RELU6 ? 6.f : __int_as_float_host(0x7f800000);
         const size_t total = (size_t)p.M * (a.N / 4);
-        splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g_scratch, a.dst, a.residual, a.scale, a.shift, p.M, a.N,
-                                                                            p.k_splits, mpad * a.N, slope, clamp);
+        launch_k(splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float *)g_scratch, a.dst, a.residual,
+                 a.scale, a.shift, p.M, a.N, p.k_splits, mpad * a.N, slope, clamp);
         e = cudaGetLastError();
     }
     return e;

@@ -29,3 +29,4 @@ if "pw1" in which: run(32, 112, 160, 24, 0, 0, 48, 1)    # pw1
 if "pw3" in which: run(32, 56, 80, 96, 0, 0, 96, 1)      # pw3
 if "pw7" in which: run(32, 14, 20, 384, 0, 0, 384, 1)    # pw7
 if "h13" in which: run(32, 7, 10, 768, 0, 0, 192, 3)     # head1 3x3
+if "h23" in which: run(32, 7, 10, 128, 384, 1, 128, 3)   # head2 3x3: up(lateral 128) || x1 (384) -> 128
