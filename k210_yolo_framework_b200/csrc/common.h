@@ -44,6 +44,8 @@ struct ConvArgs {
     // first layer only: uint8 pixels + per-image maximum; the kernel feeds x = u8 / max  (tools/utils.py:405 `img / np.max(img)`)
     const unsigned char *src_u8 = nullptr;
     const int *img_max = nullptr;
+    // host copies of w / scale / shift (first conv: passed to the kernel BY VALUE, i.e. through the constant bank)
+    const float *w_host = nullptr, *scale_host = nullptr, *shift_host = nullptr;
 };
 
 struct DwArgs {

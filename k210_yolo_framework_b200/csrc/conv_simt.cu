@@ -288,73 +288,119 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const DwArgs a) {
     }
 }
 
-// First convolution of every network: 3x3, Cin = 3, Cout in {16, 24, 32}.  One thread = one output pixel, all
-// output channels; the 27 x COUT weights sit in shared memory and are read as warp-wide broadcasts.
-template <int COUT, bool U8>
-__global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a) {
+// First convolution of every network: 3x3, Cin = 3, Cout in {16, 24, 32}.  One thread = one output pixel, all output
+// channels.  The 27 x COUT weights and the folded BN constants travel BY VALUE in the kernel parameters, i.e. in the
+// constant bank: every FFMA takes its weight as a constant operand and no load instruction is issued for it (with the
+// weights in shared memory the 162 warp-wide LDS.128 broadcasts per pixel — 4 data-path cycles each — made the kernel
+// L1/shared-pipe bound at 87 %, ncu profiles/r01_ncu_full_misc_v4.csv).  A CTA owns 128 consecutive pixels of the
+// flattened [B*OH*OW] output, one contiguous 128*COUT*4-byte block: results are staged in shared memory and written
+// with fully coalesced 16-byte stores.
+template <int COUT>
+struct FirstConvConsts {
+    float w[27 * COUT];  // [(ky,kx,ci)][n]
+    float scale[COUT], shift[COUT];
+};
+
+template <int COUT, bool U8, int ACT>  // ACT: compile-time activation (ACT_LEAKY / ACT_RELU6), -1 = read a.act at run time
+__global__ void __launch_bounds__(128) first_conv3x3_kernel(const ConvArgs a, const FirstConvConsts<COUT> cw) {
     pdl_trigger();
-    __shared__ __align__(16) float ws[27 * COUT];
-    __shared__ __align__(16) float sc[COUT], sh[COUT];
-    __shared__ float lut[U8 ? 256 : 1];  // u8 -> u8 / max(image) with the IEEE division the reference's float32 cast implies
-    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) ws[i] = a.w[i];
-    if (threadIdx.x < COUT) {
-        sc[threadIdx.x] = a.scale[threadIdx.x];
-        sh[threadIdx.x] = a.shift[threadIdx.x];
-    }
-    const int row = blockIdx.y;
-    const int oy = row % a.OH, b = row / a.OH;
-    pdl_wait();  // weights above are constants; the image maximum / input / output below belong to the stream order
+    constexpr int PITCH = COUT + 4;  // floats; conflict-free float4 rows
+    __shared__ __align__(16) float stage[128 * PITCH];
+    __shared__ float lut[U8 ? 512 : 1];  // u8 -> u8 / max(image) (IEEE division, as the reference's float32 cast implies) for the
+                                         // two images a CTA's pixel range can touch
+    const int per_img = a.OH * a.OW;
+    const long long total = (long long)a.B * per_img;
+    const long long p0 = (long long)blockIdx.x * 128;
+    const int b0 = (int)(p0 / per_img);
+    pdl_wait();  // the image maximum / input / output below belong to the stream order
     if (U8) {
-        const float mx = (float)a.img_max[b];
-        for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = __fdiv_rn((float)v, mx);
+        const float mx0 = (float)a.img_max[b0];
+        const float mx1 = (float)a.img_max[min(b0 + 1, a.B - 1)];
+        for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+            lut[v] = __fdiv_rn((float)v, mx0);
+            lut[256 + v] = __fdiv_rn((float)v, mx1);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ox >= a.OW) return;
-    const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
-    float in[27];
+    const long long pix = p0 + threadIdx.x;
+    if (pix < total) {
+        const int b = (int)(pix / per_img);
+        const int rem = (int)(pix - (long long)b * per_img);
+        const int oy = rem / a.OW, ox = rem - oy * a.OW;
+        const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
+        const bool far = U8 && b - b0 > 1;  // images smaller than 128 output pixels: divide directly
+        const float mxf = far ? (float)a.img_max[b] : 1.f;
+        const float *lt = lut + (far ? 0 : (b - b0) * 256);
+        float in[27];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int iy = iy0 + ky;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = iy0 + ky;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int ix = ix0 + kx;
-            const bool ok = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-            if (U8) {
-                const unsigned char *p8 = a.src_u8 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ix0 + kx;
+                const bool ok = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+                if (U8) {
+                    const unsigned char *p8 = a.src_u8 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci) in[(ky * 3 + kx) * 3 + ci] = ok ? lut[__ldg(p8 + ci)] : 0.f;
-            } else {
-                const float *p = a.src0 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const int v = ok ? (int)__ldg(p8 + ci) : 0;
+                        in[(ky * 3 + kx) * 3 + ci] = !ok ? 0.f : (far ? __fdiv_rn((float)v, mxf) : lt[v]);
+                    }
+                } else {
+                    const float *p = a.src0 + ((size_t)(b * a.H + iy) * a.W + ix) * 3;
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci) in[(ky * 3 + kx) * 3 + ci] = ok ? __ldg(p + ci) : 0.f;
+                    for (int ci = 0; ci < 3; ++ci) in[(ky * 3 + kx) * 3 + ci] = ok ? __ldg(p + ci) : 0.f;
+                }
             }
         }
-    }
-    float acc[COUT];
+        float acc[COUT];
 #pragma unroll
-    for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
+        for (int n = 0; n < COUT; ++n) acc[n] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
+        for (int k = 0; k < 27; ++k) {
+#pragma unroll
+            for (int n = 0; n < COUT; ++n) acc[n] = fmaf(in[k], cw.w[k * COUT + n], acc[n]);
+        }
+        const int act = ACT >= 0 ? ACT : a.act;
 #pragma unroll
         for (int n = 0; n < COUT; n += 4) {
-            const float4 wv = *reinterpret_cast<const float4 *>(&ws[k * COUT + n]);
-            acc[n] = fmaf(in[k], wv.x, acc[n]);
-            acc[n + 1] = fmaf(in[k], wv.y, acc[n + 1]);
-            acc[n + 2] = fmaf(in[k], wv.z, acc[n + 2]);
-            acc[n + 3] = fmaf(in[k], wv.w, acc[n + 3]);
+            float4 o;
+            o.x = apply_act(fmaf(acc[n], cw.scale[n], cw.shift[n]), act, a.alpha);
+            o.y = apply_act(fmaf(acc[n + 1], cw.scale[n + 1], cw.shift[n + 1]), act, a.alpha);
+            o.z = apply_act(fmaf(acc[n + 2], cw.scale[n + 2], cw.shift[n + 2]), act, a.alpha);
+            o.w = apply_act(fmaf(acc[n + 3], cw.scale[n + 3], cw.shift[n + 3]), act, a.alpha);
+            *reinterpret_cast<float4 *>(&stage[threadIdx.x * PITCH + n]) = o;
         }
     }
-    float *outp = a.dst + ((size_t)row * a.OW + ox) * COUT;
+    __syncthreads();
+    constexpr int Q = COUT / 4;  // float4 per pixel
+    const long long valid = (total - p0 < 128 ? total - p0 : 128) * Q;
+    float4 *outp = reinterpret_cast<float4 *>(a.dst + (size_t)p0 * COUT);
 #pragma unroll
-    for (int n = 0; n < COUT; n += 4) {
-        float4 o;
-        o.x = apply_act(fmaf(acc[n], sc[n], sh[n]), a.act, a.alpha);
-        o.y = apply_act(fmaf(acc[n + 1], sc[n + 1], sh[n + 1]), a.act, a.alpha);
-        o.z = apply_act(fmaf(acc[n + 2], sc[n + 2], sh[n + 2]), a.act, a.alpha);
-        o.w = apply_act(fmaf(acc[n + 3], sc[n + 3], sh[n + 3]), a.act, a.alpha);
-        *reinterpret_cast<float4 *>(outp + n) = o;
+    for (int j = 0; j < Q; ++j) {
+        const int e = threadIdx.x + 128 * j;
+        if (e < valid) outp[e] = *reinterpret_cast<const float4 *>(&stage[(e / Q) * PITCH + (e % Q) * 4]);
     }
+}
+
+template <int COUT>
+cudaError_t launch_first_conv(const ConvArgs &a, cudaStream_t st) {
+    if (!a.w_host || !a.scale_host || !a.shift_host) return cudaErrorInvalidValue;
+    FirstConvConsts<COUT> cw;
+    memcpy(cw.w, a.w_host, sizeof(cw.w));
+    memcpy(cw.scale, a.scale_host, sizeof(cw.scale));
+    memcpy(cw.shift, a.shift_host, sizeof(cw.shift));
+    const dim3 grid((unsigned)(((long long)a.B * a.OH * a.OW + 127) / 128));
+#define K2Y_FIRST(U8V, ACTV) launch_k(first_conv3x3_kernel<COUT, U8V, ACTV>, grid, dim3(128), 0, st, a, cw)
+    if (a.src_u8) {
+        if (a.act == ACT_LEAKY) return K2Y_FIRST(true, ACT_LEAKY);
+        if (a.act == ACT_RELU6) return K2Y_FIRST(true, ACT_RELU6);
+        return K2Y_FIRST(true, -1);
+    }
+    if (a.act == ACT_LEAKY) return K2Y_FIRST(false, ACT_LEAKY);
+    if (a.act == ACT_RELU6) return K2Y_FIRST(false, ACT_RELU6);
+    return K2Y_FIRST(false, -1);
+#undef K2Y_FIRST
 }
 
 // Per-image maximum of a uint8 batch (np.max(img) of tools/utils.py:405): grid = (chunks, B), atomicMax into int[B].
@@ -413,16 +459,8 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const PoolArgs a) {
 cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
     const int M = a.B * a.OH * a.OW;
     if (a.kh == 3 && a.kw == 3 && a.C0 == 3 && a.C1 == 0 && !a.up0 && !a.residual && (a.N == 16 || a.N == 24 || a.N == 32)) {
-        dim3 grid((a.OW + 127) / 128, a.B * a.OH);
-        if (a.src_u8) {
-            if (a.N == 16) launch_k(first_conv3x3_kernel<16, true>, grid, dim3(128), 0, st, a);
-            else if (a.N == 24) launch_k(first_conv3x3_kernel<24, true>, grid, dim3(128), 0, st, a);
-            else launch_k(first_conv3x3_kernel<32, true>, grid, dim3(128), 0, st, a);
-        } else {
-            if (a.N == 16) launch_k(first_conv3x3_kernel<16, false>, grid, dim3(128), 0, st, a);
-            else if (a.N == 24) launch_k(first_conv3x3_kernel<24, false>, grid, dim3(128), 0, st, a);
-            else launch_k(first_conv3x3_kernel<32, false>, grid, dim3(128), 0, st, a);
-        }
+        cudaError_t fe = a.N == 16 ? launch_first_conv<16>(a, st) : (a.N == 24 ? launch_first_conv<24>(a, st) : launch_first_conv<32>(a, st));
+        if (fe != cudaSuccess) return fe;
         return cudaGetLastError();
     }
     const bool vec = (a.C0 % 4 == 0) && (a.C1 % 4 == 0);

@@ -55,6 +55,7 @@ struct Layer {
     std::vector<float> kernel, bias, gamma, beta, mean, var;
     // device
     float *d_w = nullptr, *d_scale = nullptr, *d_shift = nullptr;
+    std::vector<float> h_scale, h_shift;  // folded BN (host copy; the first conv takes its constants by value)
     TcWeights tc;  // tensor-core packing (gemm_tc.cu)
     int fused = 0;  // last issue_layers(): 1 = this depthwise ran fused with the next 1x1 conv, 2 = this conv ran inside the previous launch
 };
@@ -409,6 +410,9 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
         a.w = L.d_w;
         a.scale = L.d_scale;
         a.shift = L.d_shift;
+        a.w_host = L.kernel.data();
+        a.scale_host = L.h_scale.data();
+        a.shift_host = L.h_shift.data();
         a.B = batch;
         a.H = L.up0 ? s0.h * 2 : s0.h;
         a.W = L.up0 ? s0.w * 2 : s0.w;
@@ -714,6 +718,8 @@ extern "C" int k2y_net_finalize(k2y_net *net) {
         K2Y_CUDA_CHECK(cudaMemcpy(L.d_w, L.kernel.data(), L.kernel.size() * sizeof(float), cudaMemcpyHostToDevice));
         K2Y_CUDA_CHECK(cudaMemcpy(L.d_scale, scale.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
         K2Y_CUDA_CHECK(cudaMemcpy(L.d_shift, shift.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
+        L.h_scale = scale;
+        L.h_shift = shift;
         if (L.kind == L_CONV) {
             int rc = tc_pack(L.tc, L.kernel.data(), L.kh * L.kw * L.cin, L.cout);
             if (rc != K2Y_OK) return rc;
@@ -1033,6 +1039,9 @@ extern "C" int k2y_conv2d(const float *src0_dev, const float *src1_dev, const fl
     a.w = d_w;
     a.scale = d_sc;
     a.shift = d_sh;
+    a.w_host = kernel_host;
+    a.scale_host = scale_host;
+    a.shift_host = shift_host;
     TcWeights tw;
     int rc = K2Y_OK;
     cudaError_t e = cudaSuccess;
