@@ -286,6 +286,17 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// wait + (trace mode) add the cycles spent waiting to trace slot `slot` of this CTA; `who` = this thread is the one that reports
+#define K2Y_TIMED_WAIT(bar, parity, slot, who)                                            \
+    do {                                                                                 \
+        if (p.trace) {                                                                   \
+            const long long _t0 = clock64();                                             \
+            mbar_wait((bar), (parity));                                                  \
+            if (who) p.trace[(size_t)blockIdx.x * 64 + (slot)] += clock64() - _t0;       \
+        } else {                                                                         \
+            mbar_wait((bar), (parity));                                                  \
+        }                                                                                \
+    } while (0)
 #define K2Y_TRACE(slot)                                                                  \
     do {                                                                                 \
         if (p.trace) p.trace[(size_t)blockIdx.x * 64 + (slot)] = gtime();                \
@@ -446,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of this epilogue group only
                 else asm volatile("bar.sync 3, 128;" ::: "memory");
             }
-            mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
+            K2Y_TIMED_WAIT(smem_u32(&bars->tmem_full[a]), aph, 56, (g == 0 && ew == 0 && lane == 0));
             if (t == cluster_id && tracer) K2Y_TRACE(8);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)p.BN;
@@ -586,7 +597,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int mt = mp * p.cluster + crank;
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                    K2Y_TIMED_WAIT(smem_u32(&bars->empty[s]), ph ^ 1u, 57, (warp == 0 && lane == 0));
                     const uint32_t fb = smem_u32(&bars->full_b[s]);
                     if (elect_one_sync()) {
                     mbar_arrive_expect_tx(fb, tx);
@@ -624,15 +635,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t ph = 0, acc_it = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++acc_it) {
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-                mbar_wait(smem_u32(&bars->tmem_empty[a]), aph ^ 1u);
+                K2Y_TIMED_WAIT(smem_u32(&bars->tmem_empty[a]), aph ^ 1u, 58, (lane == 0));
                 tc_fence_after();
                 const uint32_t d = tmem_base + a * (uint32_t)p.BN;
                 const int ks = t % p.k_splits;
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    if (!(p.dbg & 8)) mbar_wait(smem_u32(&bars->full_b[s]), ph);
+                    if (!(p.dbg & 8)) K2Y_TIMED_WAIT(smem_u32(&bars->full_b[s]), ph, 59, (lane == 0));
                     if (t == cluster_id && kb == kb0 && lane == 0) K2Y_TRACE(4);
-                    if (use_conv && !(p.dbg & 8)) mbar_wait(smem_u32(&bars->conv[s]), ph);
+                    if (use_conv && !(p.dbg & 8)) K2Y_TIMED_WAIT(smem_u32(&bars->conv[s]), ph, 60, (lane == 0));
                     if (t == cluster_id && kb == kb0 && lane == 0) K2Y_TRACE(5);
                     tc_fence_after();
                     if (elect_one_sync()) {
@@ -816,7 +827,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int ks = t % p.k_splits;
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(smem_u32(GATHER ? &bars->full_a[s] : &bars->full_b[s]), ph);
+                    K2Y_TIMED_WAIT(smem_u32(GATHER ? &bars->full_a[s] : &bars->full_b[s]), ph, 61, (ct == 0));
                     if (t == cluster_id && kb - kb0 < 8 && ct == 0) K2Y_TRACE(16 + (kb - kb0) * 4 + 1);
                     if (p.bf16) {
                         // thread = GEMM row: 64 fp32 -> bf16 hi plane (32 columns) + bf16 mid plane (32 columns) in TMEM
@@ -1335,6 +1346,8 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         // per-k-block pipeline of CTA 0's first tile: tma issue / landed (converter sees it) / converted / mma issued / slot free again
         fprintf(stderr, "[tc-trace] epilogue chunk cycles: tmem_ld+wait=%lld math=%lld wait_read=%lld sts+fence=%lld tma_issue=%lld\n", h[48],
                 h[49], h[50], h[51], h[52]);
+        fprintf(stderr, "[tc-trace] wait cycles (cta 0): epilogue<-accumulator %lld | tma<-free stage %lld | mma<-free accumulator %lld, <-weights %lld, <-converter %lld | converter<-A tile %lld\n",
+                h[56], h[57], h[58], h[59], h[60], h[61]);
         if (p.dw) fprintf(stderr, "[tc-trace] dw producer (cta 0): wait_empty=%lld produce=%lld cycles over %lld tiles\n", h[53], h[54], h[55]);
         fprintf(stderr, "[tc-trace] kb: tma_issue landed converted mma_issued\n");
         for (int kb = 0; kb < 8; ++kb) {

@@ -56,6 +56,10 @@ struct Layer {
     // device
     float *d_w = nullptr, *d_scale = nullptr, *d_shift = nullptr;
     std::vector<float> h_scale, h_shift;  // folded BN (host copy; the first conv takes its constants by value)
+    // "pixel pair" form of a narrow 1x1 conv (Cin <= 32): [M][K] x [K][N] run as [M/2][2K] x blockdiag(W, W)[2K][2N] — the same
+    // memory on both sides, half as many 128-row tiles, full-width TMA boxes (gemm_tc.cu per-tile costs dominate these layers)
+    TcWeights tc2;
+    float *d_scale2 = nullptr, *d_shift2 = nullptr;
     TcWeights tc;  // tensor-core packing (gemm_tc.cu)
     int fused = 0;  // last issue_layers(): 1 = this depthwise ran fused with the next 1x1 conv, 2 = this conv ran inside the previous launch
 };
@@ -447,7 +451,22 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
                 a.src_u8 = n->x_u8;
                 a.img_max = n->img_max;
             }
-            if (n->math != K2Y_MATH_FP32_SIMT && tc_supported(a, L.tc)) {
+            const long long Mrows = (long long)batch * d.h * d.w;
+            ConvArgs pa = a;  // pixel-pair form (see Layer::tc2)
+            const bool pair = n->math != K2Y_MATH_FP32_SIMT && L.tc2.d_hi && L.d_scale2 && (Mrows % 2) == 0 && !getenv("K2Y_NO_PAIR");
+            if (pair) {
+                pa.B = 1;
+                pa.H = pa.OH = 1;
+                pa.W = pa.OW = (int)(Mrows / 2);
+                pa.C0 = 2 * L.cin;
+                pa.N = 2 * L.cout;
+                pa.scale = L.d_scale2;
+                pa.shift = L.d_shift2;
+            }
+            if (pair && tc_supported(pa, L.tc2)) {
+                e = launch_conv_tc(pa, L.tc2, n->math, st);
+                n->launches += tc_launch_count(pa, L.tc2, n->math);
+            } else if (n->math != K2Y_MATH_FP32_SIMT && tc_supported(a, L.tc)) {
                 e = launch_conv_tc(a, L.tc, n->math, st);
                 n->launches += tc_launch_count(a, L.tc, n->math);
             } else {
@@ -587,6 +606,10 @@ extern "C" int k2y_net_destroy(k2y_net *net) {
         cudaFree(L.d_scale);
         cudaFree(L.d_shift);
         tc_free(L.tc);
+        tc_free(L.tc2);
+        cudaFree(L.d_scale2);
+        cudaFree(L.d_shift2);
+        L.d_scale2 = L.d_shift2 = nullptr;
     }
     delete net;
     return K2Y_OK;
@@ -723,6 +746,29 @@ extern "C" int k2y_net_finalize(k2y_net *net) {
         if (L.kind == L_CONV) {
             int rc = tc_pack(L.tc, L.kernel.data(), L.kh * L.kw * L.cin, L.cout);
             if (rc != K2Y_OK) return rc;
+            tc_free(L.tc2);
+            cudaFree(L.d_scale2);
+            cudaFree(L.d_shift2);
+            L.d_scale2 = L.d_shift2 = nullptr;
+            if (L.kh == 1 && L.stride == 1 && L.src1 < 0 && !L.up0 && L.cin <= 32 && (L.cin % 2) == 0 && L.cout <= 128 && (L.cout % 4) == 0) {
+                const int K = L.cin, N = L.cout;
+                std::vector<float> wd((size_t)4 * K * N, 0.f), sc2(2 * N), sh2(2 * N);
+                for (int k = 0; k < K; ++k)
+                    for (int nn = 0; nn < N; ++nn) {
+                        wd[(size_t)k * 2 * N + nn] = L.kernel[(size_t)k * N + nn];
+                        wd[(size_t)(K + k) * 2 * N + N + nn] = L.kernel[(size_t)k * N + nn];
+                    }
+                for (int nn = 0; nn < N; ++nn) {
+                    sc2[nn] = sc2[N + nn] = scale[nn];
+                    sh2[nn] = sh2[N + nn] = shift[nn];
+                }
+                rc = tc_pack(L.tc2, wd.data(), 2 * K, 2 * N);
+                if (rc != K2Y_OK) return rc;
+                K2Y_CUDA_CHECK(cudaMalloc(&L.d_scale2, 2 * N * sizeof(float)));
+                K2Y_CUDA_CHECK(cudaMalloc(&L.d_shift2, 2 * N * sizeof(float)));
+                K2Y_CUDA_CHECK(cudaMemcpy(L.d_scale2, sc2.data(), 2 * N * sizeof(float), cudaMemcpyHostToDevice));
+                K2Y_CUDA_CHECK(cudaMemcpy(L.d_shift2, sh2.data(), 2 * N * sizeof(float), cudaMemcpyHostToDevice));
+            }
         }
     }
     net->finalized = true;

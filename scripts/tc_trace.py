@@ -30,3 +30,5 @@ if "pw3" in which: run(32, 56, 80, 96, 0, 0, 96, 1)      # pw3
 if "pw7" in which: run(32, 14, 20, 384, 0, 0, 384, 1)    # pw7
 if "h13" in which: run(32, 7, 10, 768, 0, 0, 192, 3)     # head1 3x3
 if "h23" in which: run(32, 7, 10, 128, 384, 1, 128, 3)   # head2 3x3: up(lateral 128) || x1 (384) -> 128
+if "pw1p" in which: run(1, 1, 286720, 48, 0, 0, 96, 1)   # conv_pw_1 in pixel-pair form: [M/2][48] x blockdiag -> [M/2][96]
+if "pw2" in which: run(32, 56, 80, 48, 0, 0, 96, 1)      # pw2
