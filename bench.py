@@ -161,6 +161,15 @@ def cpu_reference_throughput(budget_s=15.0, min_reps=2):
                           f"{threads} torch threads (best of a sweep) of {avail} usable cores")
 
 
+_JSON_OUT = None
+
+
+def emit(line: str) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -190,7 +199,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     ips = BATCH * args.steps / dt
     sample = f"{args.steps} steps x batch {BATCH}; TF-CPU stand-in (TF 1.14 unavailable offline): oracle torch-CPU (oneDNN, channels_last) fp32 convs + numpy NMS; {threads} torch threads (best of a sweep) of {avail} usable cores"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -378,7 +387,7 @@ def run_ours(args):
             "detect_ms": det_ms,
             "top_launches": sorted(({"name": a["name"], "ms": round(a["ms"], 4)} for a in acc), key=lambda a: -a["ms"])[:6],
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -394,6 +403,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    # version banner there on every rank): keep a private handle on the real stdout for the JSON line and point fd 1 at stderr.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
