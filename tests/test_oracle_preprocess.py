@@ -66,3 +66,34 @@ def test_process_img_is_letterbox_over_max(people_u8):
     lb = preprocess_ref.letterbox(people_u8, (224, 320))
     assert x.dtype == np.float64 and x.max() == 1.0
     np.testing.assert_array_equal(x, lb / lb.max())
+
+
+def test_people_golden_fixture_reproduced(people_u8, golden_weights, voc_anchors):
+    """tests/golden/people_golden.json (made by tests/golden/make_golden.py --people-only): letterbox bytes, and the five
+    class-14 detections of asset/people_res.jpg from the oracle network + KERAS-dialect decode on the letterboxed image."""
+    import hashlib
+    import json
+    import os
+
+    from oracle import decode_ref, keras_ref
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "people_golden.json")) as fh:
+        gold = json.load(fh)
+    lb = preprocess_ref.letterbox(people_u8, (224, 320))
+    assert hashlib.sha256(lb.tobytes()).hexdigest() == gold["letterbox_sha256"]
+    x = (lb / np.max(lb)).astype(np.float32)[None]
+    heads = keras_ref.forward("yolo_mobilev1", golden_weights, x, alpha=0.75)
+    h = decode_ref.HelperRef(voc_anchors, [224, 320], [7, 10, 14, 20], 20)
+    yp = [hd[0].reshape(hd.shape[1], hd.shape[2], 3, 25) for hd in heads]
+    det = decode_ref.detect_image(yp, h, [224, 320], people_u8.shape[:2], 0.7, 0.5)
+    assert [(int(d[0]), int(d[1])) for d in det] == [(d[0], d[1]) for d in gold["detections"]]
+    for d, g in zip(det, gold["detections"]):
+        assert abs(float(d[2]) - g[2]) < 1e-4
+        assert np.abs(np.array([float(v) for v in d[3:]]) - np.array(g[3:])).max() < 1e-2
+    # SURVEY.md §8c secondary known answer (cv2-based there, so only loosely comparable): same five boxes, class 14
+    assert [d[1] for d in gold["detections"]] == [637, 778, 745, 676, 590]
+    survey = {637: (0.998, [98.7, 20.5, 316.3, 92.5]), 778: (0.987, [127.7, 206.6, 373.2, 282.0]), 745: (0.978, [139.6, 456.8, 312.8, 502.8]),
+              676: (0.941, [147.7, 361.6, 273.1, 415.1]), 590: (0.802, [123.4, 128.9, 217.9, 162.5])}
+    for g in gold["detections"]:
+        sc, box = survey[g[1]]
+        assert abs(g[2] - sc) < 0.02 and np.abs(np.array(g[3:]) - np.array(box)).max() < 0.5
