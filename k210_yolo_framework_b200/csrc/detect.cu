@@ -116,22 +116,8 @@ __device__ __forceinline__ void warp_sort_desc_mem(unsigned long long *keys, int
     }
 }
 
-// tf.image.non_max_suppression IoU on (ymin,xmin,ymax,xmax) boxes.
-__device__ __forceinline__ float iou_yxyx(const float4 a, const float4 b) {
-    const float ymin_a = fminf(a.x, a.z), ymax_a = fmaxf(a.x, a.z);
-    const float xmin_a = fminf(a.y, a.w), xmax_a = fmaxf(a.y, a.w);
-    const float ymin_b = fminf(b.x, b.z), ymax_b = fmaxf(b.x, b.z);
-    const float xmin_b = fminf(b.y, b.w), xmax_b = fmaxf(b.y, b.w);
-    const float area_a = __fmul_rn(__fsub_rn(ymax_a, ymin_a), __fsub_rn(xmax_a, xmin_a));
-    const float area_b = __fmul_rn(__fsub_rn(ymax_b, ymin_b), __fsub_rn(xmax_b, xmin_b));
-    if (area_a <= 0.f || area_b <= 0.f) return 0.f;
-    const float iy = fmaxf(__fsub_rn(fminf(ymax_a, ymax_b), fmaxf(ymin_a, ymin_b)), 0.f);
-    const float ix = fmaxf(__fsub_rn(fminf(xmax_a, xmax_b), fmaxf(xmin_a, xmin_b)), 0.f);
-    const float inter = __fmul_rn(iy, ix);
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-}
-
-// `iou_yxyx(a, b) > thr` without the division in the common case: inter/uni > thr  <=>  inter > thr*uni (uni > 0).
+// tf.image.non_max_suppression's test `IoU(a, b) > thr` on (ymin,xmin,ymax,xmax) boxes (zero-area boxes -> IoU 0), without
+// the division in the common case: inter/uni > thr  <=>  inter > thr*uni (uni > 0).
 // The product form is only trusted outside a 1e-6 relative margin (>> the 3 roundings involved); inside it the
 // exact IEEE division decides, so the boolean is bit-identical to the reference's `iou > iou_threshold`.
 __device__ __forceinline__ bool iou_yxyx_gt(const float4 a, const float4 b, float thr) {

@@ -35,7 +35,6 @@ namespace {
 
 constexpr int BM = 128;          // rows per tile (UMMA_M)
 constexpr int BK = 32;           // fp32 per k-block = 128 bytes = one SWIZZLE_128B row
-constexpr int UMMA_K = 8;        // tf32
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
 constexpr int NUM_THREADS = 14 * 32;
 constexpr int MAX_STAGES = 8;
@@ -236,12 +235,6 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 // D = F32, A = B = BF16 (kind::f16), K-major B, dense.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-// fp32 -> bf16 bits, round to nearest even (finite inputs)
-__device__ __forceinline__ uint32_t bf16_rne_bits(float x) {
-    const uint32_t u = __float_as_uint(x);
-    return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
 }
 
 // two fp32 -> packed bf16x2 (round to nearest even): lo element in bits [0,16), hi element in [16,32)
