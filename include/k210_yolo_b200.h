@@ -166,6 +166,25 @@ int k2y_region_run(const k2y_region_cfg *cfg, const float *in_dev, int batch, fl
                    float *probs_dev, float *boxes_dev, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Operator-level pieces of the reference's decode loop, for callers that keep keras_inference.py:94-135 and swap one
+ * operator at a time (device pointers; same arithmetic as k2y_detect_keras):
+ *   k2y_xywh_to_all  = tf_xywh_to_all (tools/utils.py:524-547): pred_xy / pred_wh [..][h][w][A][2] contiguous ->
+ *                      xy = (sigmoid(t) + (col,row)) / (w,h), wh = exp(t) * anchor[a]   (anchors_wh_host: A (w,h) pairs)
+ *   k2y_correct_box  = correct_box (keras_inference.py:32-72): -> boxes [n][4] (ymin,xmin,ymax,xmax) in image pixels
+ *   k2y_nms_boxes    = tf.image.non_max_suppression(boxes [n][4] yxyx, scores [n], max_output_size, iou_threshold)
+ *                      (keras_inference.py:125-126): greedy, score-descending (ties: lower index first), suppress iff
+ *                      IoU > threshold; writes <= max_output_size int32 indices in selection order and their count.
+ *                      boxes_dev must be 16-byte aligned; workspace from k2y_nms_workspace_bytes.
+ * ---------------------------------------------------------------------------------------- */
+int k2y_xywh_to_all(const float *pred_xy_dev, const float *pred_wh_dev, long long n_boxes, int layer_h, int layer_w,
+                    int anchor_num, const float *anchors_wh_host, float *xy_dev, float *wh_dev, void *stream);
+int k2y_correct_box(const float *xy_dev, const float *wh_dev, long long n_boxes, float in_h, float in_w, float image_h,
+                    float image_w, float *boxes_dev, void *stream);
+int k2y_nms_workspace_bytes(int n_boxes, int max_output_size, size_t *bytes);
+int k2y_nms_boxes(const float *boxes_dev, const float *scores_dev, int n_boxes, int max_output_size, float iou_threshold,
+                  int32_t *indices_dev, int32_t *count_dev, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Pre-processing: aspect-preserving letterbox of ONE uint8 HWC RGB image on the device
  * (tools/utils.py:372-400: AffineTransform(scale, translation) + skimage warp order 1, zero fill, .astype('uint8')).
  * inv_matrix_host: the first two rows of inv([[s,0,tx],[0,s,ty],[0,0,1]]) as 6 doubles (host memory) - what

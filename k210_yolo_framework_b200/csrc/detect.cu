@@ -556,6 +556,91 @@ __global__ void __launch_bounds__(DET_THREADS) region_kernel(const RegionParams 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Operator-level entry points of the reference's decode loop (keras_inference.py:94-135), for callers that keep that loop
+// and replace one operator at a time.  Same arithmetic (intrinsics, operation order) as the fused kernel above.
+// ---------------------------------------------------------------------------------------------------------------------
+struct OpsAnchors {
+    float wh[16];  // (w, h) pairs of one layer, A <= 8
+};
+
+// tf_xywh_to_all (tools/utils.py:524-547): raw [.., h, w, A, 2] xy / wh head slices -> xy in [0, 1], wh as input fraction.
+__global__ void __launch_bounds__(256) xywh_to_all_kernel(const float2 *__restrict__ pred_xy, const float2 *__restrict__ pred_wh,
+                                                          float2 *__restrict__ xy, float2 *__restrict__ wh, long long total, int H,
+                                                          int W, int A, const OpsAnchors anc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int a = (int)(i % A);
+    const int cell = (int)((i / A) % ((long long)H * W));
+    const int col = cell % W, row = cell / W;
+    const float2 t = pred_xy[i], u = pred_wh[i];
+    float2 o;
+    o.x = __fdiv_rn(__fadd_rn(sigmoidf_ref(t.x), (float)col), (float)W);
+    o.y = __fdiv_rn(__fadd_rn(sigmoidf_ref(t.y), (float)row), (float)H);
+    xy[i] = o;
+    o.x = __fmul_rn(expf(u.x), anc.wh[2 * a]);
+    o.y = __fmul_rn(expf(u.y), anc.wh[2 * a + 1]);
+    wh[i] = o;
+}
+
+// correct_box (keras_inference.py:32-72): (xy, wh) relative to the letterboxed input -> (ymin, xmin, ymax, xmax) in pixels
+// of the original image.
+__global__ void __launch_bounds__(256) correct_box_kernel(const float2 *__restrict__ xy, const float2 *__restrict__ wh,
+                                                          float4 *__restrict__ boxes, long long total, float in_h, float in_w,
+                                                          float img_h, float img_w) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float r = fminf(__fdiv_rn(in_h, img_h), __fdiv_rn(in_w, img_w));
+    const float new_h = rintf(__fmul_rn(img_h, r)), new_w = rintf(__fmul_rn(img_w, r));
+    const float off_y = __fdiv_rn(__fdiv_rn(__fsub_rn(in_h, new_h), 2.0f), in_h);
+    const float off_x = __fdiv_rn(__fdiv_rn(__fsub_rn(in_w, new_w), 2.0f), in_w);
+    const float sc_y = __fdiv_rn(in_h, new_h), sc_x = __fdiv_rn(in_w, new_w);
+    const float2 c = xy[i], s2 = wh[i];
+    const float cy = __fmul_rn(__fsub_rn(c.y, off_y), sc_y), cx = __fmul_rn(__fsub_rn(c.x, off_x), sc_x);
+    const float hh2 = __fdiv_rn(__fmul_rn(s2.y, sc_y), 2.0f), ww2 = __fdiv_rn(__fmul_rn(s2.x, sc_x), 2.0f);
+    float4 o;
+    o.x = __fmul_rn(__fsub_rn(cy, hh2), img_h);
+    o.y = __fmul_rn(__fsub_rn(cx, ww2), img_w);
+    o.z = __fmul_rn(__fadd_rn(cy, hh2), img_h);
+    o.w = __fmul_rn(__fadd_rn(cx, ww2), img_w);
+    boxes[i] = o;
+}
+
+// tf.image.non_max_suppression(boxes, scores, max_output_size, iou_threshold) (score_threshold = -inf): one warp sorts
+// every box by (score desc, index asc) and runs the greedy selection, lanes testing the kept boxes in parallel.
+__device__ __forceinline__ unsigned long long pack_key_any(float score, int idx) {
+    unsigned u = __float_as_uint(score);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // total order of finite floats and infinities as unsigned
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)idx);
+}
+
+__global__ void __launch_bounds__(32) nms_boxes_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores, int n, int P,
+                                                       int max_out, float thr, unsigned long long *keys, float4 *kept, float *kept_area,
+                                                       int *__restrict__ out_idx, int *__restrict__ out_count) {
+    const int lane = threadIdx.x;
+    for (int i = lane; i < P; i += 32) keys[i] = i < n ? pack_key_any(scores[i], i) : 0ull;
+    __syncwarp();
+    warp_sort_desc_mem(keys, P, lane);
+    int nsel = 0;
+    for (int t = 0; t < n && nsel < max_out; ++t) {
+        const int idx = key_index(keys[t]);
+        float area;
+        const float4 c = norm_box(boxes[idx], area);
+        bool hit = false;
+        for (int j = lane; j < nsel; j += 32) hit = hit || iou_norm_gt(c, area, kept[j], kept_area[j], thr);
+        if (!__any_sync(FULL, hit)) {
+            if (lane == 0) {
+                kept[nsel] = c;
+                kept_area[nsel] = area;
+                out_idx[nsel] = idx;
+            }
+            ++nsel;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) *out_count = nsel;
+}
+
 inline int next_pow2(int v) {
     int p = 64;
     while (p < v) p <<= 1;
@@ -729,6 +814,69 @@ extern "C" int k2y_region_run(const k2y_region_cfg *cfg, const float *in_dev, in
     ws += align256((size_t)batch * p.C * p.P * sizeof(unsigned long long));
     p.kept = (int *)ws;
     region_kernel<<<batch, DET_THREADS, 0, (cudaStream_t)stream>>>(p);
+    K2Y_CUDA_CHECK(cudaGetLastError());
+    return K2Y_OK;
+}
+
+extern "C" int k2y_xywh_to_all(const float *pred_xy_dev, const float *pred_wh_dev, long long n_boxes, int layer_h, int layer_w,
+                               int anchor_num, const float *anchors_wh_host, float *xy_dev, float *wh_dev, void *stream) {
+    if (!pred_xy_dev || !pred_wh_dev || !xy_dev || !wh_dev || !anchors_wh_host || n_boxes <= 0 || layer_h <= 0 || layer_w <= 0 ||
+        anchor_num < 1 || anchor_num > 8 || (n_boxes % ((long long)layer_h * layer_w * anchor_num)) != 0) {
+        set_error("k2y_xywh_to_all: bad arguments (n_boxes must be a multiple of layer_h*layer_w*anchor_num, anchor_num 1..8)");
+        return K2Y_ERR_INVALID;
+    }
+    OpsAnchors anc;
+    memset(&anc, 0, sizeof(anc));
+    for (int i = 0; i < 2 * anchor_num; ++i) anc.wh[i] = anchors_wh_host[i];
+    xywh_to_all_kernel<<<(unsigned)((n_boxes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(pred_xy_dev), reinterpret_cast<const float2 *>(pred_wh_dev), reinterpret_cast<float2 *>(xy_dev),
+        reinterpret_cast<float2 *>(wh_dev), n_boxes, layer_h, layer_w, anchor_num, anc);
+    K2Y_CUDA_CHECK(cudaGetLastError());
+    return K2Y_OK;
+}
+
+extern "C" int k2y_correct_box(const float *xy_dev, const float *wh_dev, long long n_boxes, float in_h, float in_w, float image_h,
+                               float image_w, float *boxes_dev, void *stream) {
+    if (!xy_dev || !wh_dev || !boxes_dev || n_boxes <= 0 || !(in_h > 0.f) || !(in_w > 0.f) || !(image_h > 0.f) || !(image_w > 0.f)) {
+        set_error("k2y_correct_box: bad arguments");
+        return K2Y_ERR_INVALID;
+    }
+    correct_box_kernel<<<(unsigned)((n_boxes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(xy_dev), reinterpret_cast<const float2 *>(wh_dev), reinterpret_cast<float4 *>(boxes_dev), n_boxes,
+        in_h, in_w, image_h, image_w);
+    K2Y_CUDA_CHECK(cudaGetLastError());
+    return K2Y_OK;
+}
+
+extern "C" int k2y_nms_workspace_bytes(int n_boxes, int max_output_size, size_t *bytes) {
+    if (!bytes || n_boxes < 0 || max_output_size < 0) {
+        set_error("k2y_nms_workspace_bytes: bad arguments");
+        return K2Y_ERR_INVALID;
+    }
+    const size_t P = (size_t)next_pow2(n_boxes);
+    const size_t keep = (size_t)(max_output_size < n_boxes ? max_output_size : n_boxes);
+    *bytes = align256(P * sizeof(unsigned long long)) + align256(keep * sizeof(float4)) + align256(keep * sizeof(float)) + 256;
+    return K2Y_OK;
+}
+
+extern "C" int k2y_nms_boxes(const float *boxes_dev, const float *scores_dev, int n_boxes, int max_output_size, float iou_threshold,
+                             int32_t *indices_dev, int32_t *count_dev, void *workspace, size_t workspace_bytes, void *stream) {
+    size_t need = 0;
+    int rc = k2y_nms_workspace_bytes(n_boxes, max_output_size, &need);
+    if (rc != K2Y_OK) return rc;
+    if (!count_dev || !workspace || workspace_bytes < need || (n_boxes > 0 && (!boxes_dev || !scores_dev)) ||
+        (n_boxes > 0 && max_output_size > 0 && !indices_dev) || (((uintptr_t)boxes_dev) & 15) != 0) {
+        set_error("k2y_nms_boxes: null / misaligned pointer or workspace too small (%zu < %zu)", workspace_bytes, need);
+        return K2Y_ERR_INVALID;
+    }
+    const int P = next_pow2(n_boxes);
+    const size_t keep = (size_t)(max_output_size < n_boxes ? max_output_size : n_boxes);
+    char *w = reinterpret_cast<char *>(workspace);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(w);
+    float4 *kept = reinterpret_cast<float4 *>(w + align256((size_t)P * sizeof(unsigned long long)));
+    float *kept_area = reinterpret_cast<float *>(reinterpret_cast<char *>(kept) + align256(keep * sizeof(float4)));
+    nms_boxes_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(boxes_dev), scores_dev, n_boxes, P,
+                                                         (int)keep, iou_threshold, keys, kept, kept_area, indices_dev, count_dev);
     K2Y_CUDA_CHECK(cudaGetLastError());
     return K2Y_OK;
 }
