@@ -165,6 +165,12 @@ int k2y_region_workspace_bytes(const k2y_region_cfg *cfg, int batch, size_t *byt
 int k2y_region_run(const k2y_region_cfg *cfg, const float *in_dev, int batch, float *out_dev /* activations, may be NULL */,
                    float *probs_dev, float *boxes_dev, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Diagnostics: the tile planner of the tensor-core conv kernel for a GEMM of M x K x N (ksize 1 or 3; K = ksize^2 * Cin).
+ * Host-only (assumes a B200 when no device is initialised): tile width, split-K factor, pipeline stages, CTA-pair mode
+ * and the arithmetic mode the layer really runs in. */
+int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *bn, int *k_splits, int *stages, int *cluster,
+                int *effective_math);
+
 /* ------------------------------------------------------------------------------------------
  * Operator-level pieces of the reference's decode loop, for callers that keep keras_inference.py:94-135 and swap one
  * operator at a time (device pointers; same arithmetic as k2y_detect_keras):

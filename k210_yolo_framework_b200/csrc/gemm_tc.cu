@@ -1058,7 +1058,7 @@ void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int 
             if (force && sp != atoi(force) && !(atoi(force) < 1 && sp == 1)) continue;
             if (sp > 1) {
                 if ((N & 3) != 0 || N > ID_LEN || nkb / sp < 12) continue;
-                if ((size_t)sp * m_tiles * BM * N * sizeof(float) > g_scratch_bytes) continue;
+                if ((size_t)sp * m_tiles * BM * N * sizeof(float) > (g_scratch_bytes ? g_scratch_bytes : ((size_t)64 << 20))) continue;  // 64 MB once initialised
             }
             const int kb = (nkb + sp - 1) / sp;
             const long items = (long)((m_tiles + cluster - 1) / cluster) * n_tiles * sp;  // per cluster
@@ -1372,3 +1372,36 @@ int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode) {
 }
 
 }  // namespace k2y
+
+// Host-only view of the tile planner (no GPU needed: without a device it assumes a B200 — 148 SMs, 227 KB of shared
+// memory): which tile width, split-K factor, pipeline depth and CTA-pair mode a dense conv of this GEMM shape gets.
+extern "C" int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *bn, int *k_splits, int *stages, int *cluster,
+                           int *effective_math) {
+    using namespace k2y;
+    if (M <= 0 || N <= 0 || K <= 0 || (ksize != 1 && ksize != 3) || !bn || !k_splits || !stages || !cluster || !effective_math ||
+        (math_mode != K2Y_MATH_TC_3XTF32 && math_mode != K2Y_MATH_TC_TF32 && math_mode != K2Y_MATH_TC_BF16X3)) {
+        set_error("k2y_tc_plan: bad arguments");
+        return K2Y_ERR_INVALID;
+    }
+    const bool gather = ksize == 3;
+    int mode = math_mode;
+    if (mode == K2Y_MATH_TC_BF16X3) {  // effective_mode(): same rules, expressed on (K, ksize)
+        const int cin = gather ? K / 9 : K;
+        if (!gather) mode = cin <= 32 ? K2Y_MATH_TC_3XTF32 : mode;
+        else if ((cin % 64) != 0) mode = K2Y_MATH_TC_3XTF32;
+    }
+    const bool bf = mode == K2Y_MATH_TC_BF16X3, three_x = mode != K2Y_MATH_TC_TF32;
+    const int nkb = bf ? (K + 63) / 64 : (K + BK - 1) / BK;
+    *cluster = pick_cluster(M, nkb);
+    pick_tile(M, N, nkb, three_x, bf, gather, *cluster, bn, k_splits);
+    const size_t stage_bytes = (size_t)A_TILE_BYTES * (bf ? 2 : 1) + (size_t)(*bn) * 128 * (three_x ? 2 : 1);
+    int st = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage_bytes);
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (three_x && st > (512 - 2 * *bn) / 64) st = (512 - 2 * *bn) / 64;
+    *stages = st;
+    const int kb_per_split = (nkb + *k_splits - 1) / *k_splits;
+    *k_splits = (nkb + kb_per_split - 1) / kb_per_split;
+    *effective_math = mode;
+    return K2Y_OK;
+}
+
