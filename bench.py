@@ -1,20 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the YOLOv3 inference hot path (BASELINE.json metric: images/sec, yolo_mobilev1-0.75 @320x224).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
 
-A "step" = one pass of the hot path over one batch of 32 synthetic images per GPU: network forward (one CUDA
-graph) + fused decode/NMS (+ one all-gather of the detection records when N > 1).  Weak scaling: the per-GPU
-batch is fixed, `value` is the whole-job images/sec = N*32*K / (max over ranks of the summed per-step device
-times).  Prints ONE JSON line (rank 0).
+A "step" = one pass of the hot path over one batch of synthetic images per GPU (32 for the default config 2): network
+forward (one CUDA graph) + decode scan + per-class NMS (+ ONE all-gather of the detection blocks when N > 1, on a side
+stream so that it overlaps the next step's convolutions).  Weak scaling: the per-GPU batch is fixed, `value` is the
+whole-job images/sec = N*batch*K / (max over ranks of the device time of the K steps).  Prints ONE JSON line (rank 0).
 
-  value      inputs resident in HBM, per-step CUDA events on the launching stream, L2 flushed between steps
-  e2e        same metric through DetectionPipeline.detect_host(): pinned-host input -> H2D -> step -> D2H records
-  roofline   dominant kernel of the step, timed live with CUDA events (k2y_net_profile), vs MEASURED_PEAKS.json
+  value      inputs resident in HBM; ONE CUDA-event pair around the K steps on the launching stream (the final gather is
+             waited for inside the window); steps rotate over distinct input batches totalling more than the 126 MB L2
+  e2e        same metric through DetectionPipeline.submit/collect: pinned-host uint8 input -> H2D -> step -> D2H records
+  roofline   dominant launch of the step (network layers AND the decode/NMS pair), timed live with CUDA events, vs
+             MEASURED_PEAKS.json; `traffic` from the committed ncu --set full capture (profiles/r02_traffic.json)
   cpu_baseline  the oracle ("port" of the reference TF-CPU path: torch-CPU fp32 convs + numpy NMS) on the host cores
 
-`--impl reference` times that CPU path alone (TensorFlow 1.14 cannot be installed offline; the stand-in is
-labelled as such) and prints the same JSON shape with "impl": "reference".
+`--impl reference` times that CPU path alone (TensorFlow 1.14 cannot be installed offline; the stand-in is labelled as
+such) and prints the same JSON shape with "impl": "reference".  That arm imports neither the CUDA package nor its .so.
 """
 import argparse
 import json
@@ -28,25 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+import bench_workloads as wl  # noqa: E402
 
-MODEL_DEF, ALPHA, IN_HW, CLASSES, BATCH = "yolo_mobilev1", 0.75, (224, 320), 20, 32
-OBJ_THRESH, IOU_THRESH = 0.7, 0.5
-WORKLOAD = "cfg2: yolo_mobilev1 a=0.75, 320x224 (HxW 224x320), batch 32/GPU, VOC-20 anchors, random-init detection-rich weights (seed 0)"
-FLOP_PER_IMAGE = 1.465e9
-METRIC = "images/sec @320x224 yolo_mobilev1-0.75"
-
-
-def anchors():
-    return np.load(os.path.join(ROOT, "tests", "golden", "voc_anchor.npy"))
-
-
-def bench_weights(expected):
-    from k210_yolo_framework_b200.weights import random_weights
-    return random_weights(expected, seed=0, detection_rich=True, head_bias=-0.2, head_bias_std=1.5)
-
-
-def synthetic_batch(seed, n=BATCH):
-    return np.random.default_rng(seed).random((n, IN_HW[0], IN_HW[1], 3), dtype=np.float32)
+L2_BYTES = 126 << 20
 
 
 def load_peaks():
@@ -132,33 +118,63 @@ def tune_threads(fn, avail):
     return best
 
 
-def cpu_reference_throughput(budget_s=15.0, min_reps=2):
-    """The reference's CPU path (TF-CPU stand-in: oracle torch-CPU convs + numpy NMS), all host threads."""
-    import torch
-    from oracle import decode_ref, keras_ref
-    from k210_yolo_framework_b200 import yolonet
+class CpuPath:
+    """The reference's CPU path on a bounded sample of the workload (TF-CPU stand-in: oracle torch-CPU convs + numpy NMS).
+    Touches only oracle/ and bench_workloads — never this repo's CUDA package."""
+
+    def __init__(self, cfg):
+        from oracle import decode_ref, keras_ref
+        self.cfg, self.decode_ref, self.keras_ref = cfg, decode_ref, keras_ref
+        self.w = wl.bench_weights(cfg)
+        self.h = decode_ref.HelperRef(wl.anchors(cfg), list(cfg["in_hw"]), wl.out_hw(cfg), cfg["classes"])
+        # bounded sample: about 100 GFLOP of forward work per repetition
+        self.n = int(max(1, min(cfg["batch"], 100.0 // cfg["gflop"])))
+        self.x = wl.synthetic_batch(cfg, 100, self.n)
+        self.cache = {}
+
+    def forward(self, x=None):
+        x = self.x if x is None else x
+        return self.keras_ref.forward(self.cfg["model"], self.w, x, alpha=self.cfg["alpha"], cache=self.cache, channels_last=True)
+
+    def full(self, x=None):
+        x = self.x if x is None else x
+        heads = self.forward(x)
+        return self.decode_ref.detect_batch_fast(heads, self.h, list(self.cfg["in_hw"]), [self.cfg["in_hw"]] * len(x),
+                                                 wl.OBJ_THRESH, wl.IOU_THRESH, wl.MAX_PER_CLASS)
+
+    @staticmethod
+    def rate(fn, n_images, budget_s, min_reps=2, max_reps=50):
+        times = []
+        t_end = time.perf_counter() + budget_s
+        while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < max_reps):
+            t0 = time.perf_counter()
+            fn()
+            times.append(time.perf_counter() - t0)
+        return n_images / float(np.median(times)), len(times)
+
+
+def cpu_baseline(cfg, budget_s=12.0):
     avail = usable_cpus()
-    m, _ = yolonet.yolo_mobilev1([IN_HW[0], IN_HW[1], 3], 3, CLASSES, alpha=ALPHA, max_batch=1)  # host-side graph only (names/shapes)
-    w = bench_weights(m.engine.expected_variables())
-    h = decode_ref.HelperRef(anchors(), list(IN_HW), [(IN_HW[0] // 32, IN_HW[1] // 32), (IN_HW[0] // 16, IN_HW[1] // 16)], CLASSES)
-    x = synthetic_batch(100)
-    shapes = [IN_HW] * BATCH
+    cp = CpuPath(cfg)
+    threads = tune_threads(cp.full, avail)
+    ips, reps = CpuPath.rate(cp.full, cp.n, budget_s)
+    fwd_ips, _ = CpuPath.rate(cp.forward, cp.n, budget_s / 3)
+    x1 = cp.x[:1]
+    b1_ips, _ = CpuPath.rate(lambda: cp.full(x1), 1, budget_s / 3, min_reps=3)
+    sample = (f"{reps} x {cp.n} images of the bench workload ({'the full batch' if cp.n == cfg['batch'] else 'a bounded sample of the batch'}), "
+              f"forward + decode + NMS, median; {threads} torch threads (best of a sweep) of {avail} usable cores")
+    return {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample,
+            "label": "TF-CPU stand-in (TF 1.14 unavailable offline): oracle torch-CPU (oneDNN, channels_last) fp32 convs + numpy NMS",
+            "forward_only": {"value": fwd_ips, "unit": "images/sec", "batch": cp.n},
+            "batch_1": {"value": b1_ips, "unit": "images/sec", "note": "forward + decode + NMS of ONE image per call, as keras_inference.py runs"}}
 
-    cache = {}
 
-    def one():
-        heads = keras_ref.forward(MODEL_DEF, w, x, alpha=ALPHA, cache=cache, channels_last=True)
-        return decode_ref.detect_batch_fast(heads, h, list(IN_HW), shapes, OBJ_THRESH, IOU_THRESH)
-    threads = tune_threads(one, avail)
-    times = []
-    t_end = time.perf_counter() + budget_s
-    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < 50):
-        t0 = time.perf_counter()
-        one()
-        times.append(time.perf_counter() - t0)
-    ips = BATCH / float(np.median(times))
-    return ips, threads, (f"{len(times)} x batch {BATCH} of the bench workload, forward + decode + NMS, median; "
-                          f"{threads} torch threads (best of a sweep) of {avail} usable cores")
+def workload_config(cfg, world, n_in=None, in_bytes=None):
+    """The `config` object: the workload only, identical in both arms (the driver compares them)."""
+    return {"workload": wl.workload_string(cfg), "global_batch": cfg["batch"] * world, "per_gpu_batch": cfg["batch"],
+            "obj_thresh": wl.OBJ_THRESH, "iou_thresh": wl.IOU_THRESH, "max_per_class": wl.MAX_PER_CLASS,
+            "l2": "GPU arm: steps rotate over distinct device-resident input batches totalling > 126 MiB L2, no flush inside the "
+                  "timed window; CPU arm: not applicable"}
 
 
 _JSON_OUT = None
@@ -170,47 +186,63 @@ def emit(line: str) -> None:
     out.flush()
 
 
-def run_reference(args):
+def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each step = one bounded sample (a batch of 32); steps/warmup as requested
-    import torch
-    from oracle import decode_ref, keras_ref
-    from k210_yolo_framework_b200 import yolonet
     avail = usable_cpus()
-    m, _ = yolonet.yolo_mobilev1([IN_HW[0], IN_HW[1], 3], 3, CLASSES, alpha=ALPHA, max_batch=1)
-    w = bench_weights(m.engine.expected_variables())
-    h = decode_ref.HelperRef(anchors(), list(IN_HW), [(7, 10), (14, 20)], CLASSES)
-    x = synthetic_batch(100)
-    shapes = [IN_HW] * BATCH
-
-    cache = {}
-
-    def one():
-        heads = keras_ref.forward(MODEL_DEF, w, x, alpha=ALPHA, cache=cache, channels_last=True)
-        return decode_ref.detect_batch_fast(heads, h, list(IN_HW), shapes, OBJ_THRESH, IOU_THRESH)
-    threads = tune_threads(one, avail)
+    cp = CpuPath(cfg)
+    threads = tune_threads(cp.full, avail)
     for _ in range(args.warmup):
-        one()
+        cp.full()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one()
+        cp.full()
     dt = time.perf_counter() - t0
-    ips = BATCH * args.steps / dt
-    sample = f"{args.steps} steps x batch {BATCH}; TF-CPU stand-in (TF 1.14 unavailable offline): oracle torch-CPU (oneDNN, channels_last) fp32 convs + numpy NMS; {threads} torch threads (best of a sweep) of {avail} usable cores"
+    ips = cp.n * args.steps / dt
+    sample = (f"{args.steps} steps x {cp.n} images ({'the full batch' if cp.n == cfg['batch'] else 'a bounded sample of the batch'}); "
+              f"TF-CPU stand-in (TF 1.14 unavailable offline): oracle torch-CPU (oneDNN, channels_last) fp32 convs + numpy NMS; "
+              f"{threads} torch threads (best of a sweep) of {avail} usable cores")
     emit(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": cfg["metric"], "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": BATCH, "note": "CPU only; one process on rank 0"},
+        "config": workload_config(cfg, args.gpus),
+        "arm": {"note": f"CPU only; one process on rank 0; each step = {cp.n} images", "math": "f32 (torch CPU, oneDNN)"},
         "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def run_ours(args):
+def parity_check(pipe, cfg, x_dev, budget_s=25.0):
+    """Oracle decode + NMS on the GPU's own head tensors for the bench batch: identical (class, box index) lists per image."""
+    import torch
+    from oracle import decode_ref
+    from k210_yolo_framework_b200.pipeline import DetectionPipeline
+    pipe.engine.bind_input(x_dev)
+    dets, counts = pipe.step_device()
+    pipe.wait_gathered()
+    torch.cuda.synchronize()
+    n = cfg["batch"]
+    lo = pipe.rank * n
+    got = DetectionPipeline.records(dets[lo:lo + n].clone(), counts[lo:lo + n].clone())
+    heads = [t.cpu().numpy() for t in pipe.engine.head_buffers]
+    h = decode_ref.HelperRef(wl.anchors(cfg), list(cfg["in_hw"]), wl.out_hw(cfg), cfg["classes"])
+    t_end = time.perf_counter() + budget_s
+    checked, same = 0, 0
+    for b in range(n):
+        ref = decode_ref.detect_batch_fast([hd[b:b + 1] for hd in heads], h, list(cfg["in_hw"]), [cfg["in_hw"]], wl.OBJ_THRESH,
+                                           wl.IOU_THRESH, wl.MAX_PER_CLASS)[0]
+        checked += 1
+        same += int([(d[0], d[1]) for d in got[b]] == [(d[0], d[1]) for d in ref])
+        if time.perf_counter() > t_end:
+            break
+    return {"parity_checked": bool(checked and same == checked), "images_checked": checked, "images_identical": same,
+            "what": "oracle decode + per-class NMS on the GPU's head tensors vs the CUDA records: (class, box index) lists"}
+
+
+def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
     from k210_yolo_framework_b200 import _lib
@@ -226,16 +258,18 @@ def run_ours(args):
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    math_mode = {"fp32_simt": _lib.MATH_FP32_SIMT, "tc_3xtf32": _lib.MATH_TC_3XTF32, "tc_tf32": _lib.MATH_TC_TF32,
-                 "tc_bf16x3": _lib.MATH_TC_BF16X3}[args.math]
+    math_modes = {"fp32_simt": _lib.MATH_FP32_SIMT, "tc_3xtf32": _lib.MATH_TC_3XTF32, "tc_tf32": _lib.MATH_TC_TF32,
+                  "tc_bf16x3": _lib.MATH_TC_BF16X3}
+    B, (H, W) = cfg["batch"], cfg["in_hw"]
 
-    pipe = DetectionPipeline(MODEL_DEF, IN_HW, anchors(), CLASSES, ALPHA, BATCH, OBJ_THRESH, IOU_THRESH, 30, device=local,
-                             world=world, rank=rank)
-    pipe.engine.set_weights(bench_weights(pipe.engine.expected_variables()))
-    pipe.engine.set_math(math_mode)
-    x_host = torch.from_numpy(synthetic_batch(1000 + rank)).pin_memory()
-    pipe.engine.input_buffer.copy_(x_host)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    pipe = DetectionPipeline(cfg["model"], cfg["in_hw"], wl.anchors(cfg), cfg["classes"], cfg["alpha"], B, wl.OBJ_THRESH,
+                             wl.IOU_THRESH, wl.MAX_PER_CLASS, device=local, world=world, rank=rank)
+    pipe.engine.set_weights(wl.bench_weights(cfg, pipe.engine.expected_variables()))
+    pipe.engine.set_math(math_modes[args.math])
+    # distinct device-resident input batches, together larger than L2: a step never finds its input in L2
+    in_bytes = B * H * W * 3 * 4
+    n_in = max(2, -(-int(1.3 * L2_BYTES) // in_bytes))
+    xs = [torch.from_numpy(wl.synthetic_batch(cfg, 1000 + 16 * rank + j)).cuda() for j in range(n_in)]
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -243,39 +277,45 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_steps(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            pipe.engine.bind_input(xs[i % n_in])
+            pipe.step_device()
+        pipe.wait_gathered()            # the last step's all-gather (side stream) belongs to the window
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
     # ---- device-resident timing -------------------------------------------------------------
-    for _ in range(args.warmup):
+    for j in range(n_in):               # one CUDA graph per input buffer is captured here, outside warm-up and timing
+        pipe.engine.bind_input(xs[j])
+        pipe.step_device()
+    for i in range(args.warmup):
+        pipe.engine.bind_input(xs[i % n_in])
         pipe.step_device()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
-        flush.zero_()                       # L2 flush, outside the timed window of the step
-        starts[i].record(stream)
-        pipe.step_device()
-        ends[i].record(stream)
-    barrier()
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    dev_ms = timed_steps(args.steps)
 
     # ---- end to end: pinned host input -> H2D -> step -> D2H records ----------------------------
     # streaming API (submit/collect): every step copies ITS batch from pinned host memory and brings ITS records
-    # back; copies of step i+1 overlap the kernels of step i.  Inputs rotate over 6 distinct host batches
-    # (165 MB > the 126 MB L2), so nothing a step reads is left in L2 by an earlier one.
+    # back; copies of step i+1 overlap the kernels of step i.  Host batches rotate (together > L2).
     # The user-facing input is what the reference's _read_img/_process_img hold before `img / np.max(img)`: uint8
-    # letterboxed RGB.  The normalisation runs on the GPU (fused into the first conv), so a step moves 6.9 MB over PCIe.
-    hosts = [torch.from_numpy(np.random.default_rng(2000 + 10 * rank + j).integers(0, 256, (BATCH, IN_HW[0], IN_HW[1], 3),
-                                                                                   dtype=np.uint8)).pin_memory() for j in range(24)]
-    for j in range(3):
-        pipe.collect(pipe.submit(hosts[j % len(hosts)]))
+    # letterboxed RGB.  The normalisation runs on the GPU (fused into the first conv).
+    n_host = max(3, -(-int(1.3 * L2_BYTES) // (in_bytes // 4)))
+    hosts = [torch.from_numpy(wl.synthetic_batch_u8(cfg, 2000 + 64 * rank + j)).pin_memory() for j in range(n_host)]
+    for j in range(4):
+        pipe.collect(pipe.submit(hosts[j % n_host]))
     barrier()
     t0 = time.perf_counter()
     prev = None
     for i in range(args.steps):
-        tk = pipe.submit(hosts[i % len(hosts)])
+        tk = pipe.submit(hosts[i % n_host])
         if prev is not None:
             pipe.collect(prev)
         prev = tk
@@ -283,65 +323,104 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    d2h_bytes = int(pipe.gather.bufs[0].numel() * 4)
+    n_found = int(hc.sum())
     # latency-style single call, for reference: one detect_host() = H2D + step + D2H, nothing overlapped
     t_sync = 0.0
     for i in range(5):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        pipe.detect_host(hosts[i % len(hosts)])
+        pipe.detect_host(hosts[i % n_host])
         t_sync += time.perf_counter() - t1
     e2e_sync_ms = 1000.0 * t_sync / 5
-    # same streaming loop fed with float32 host batches (27.5 MB / step over PCIe)
-    hosts_f = [x_host] + [torch.from_numpy(synthetic_batch(3000 + 10 * rank + j)).pin_memory() for j in range(5)]
+    # same streaming loop fed with float32 host batches (4x the PCIe bytes)
+    hosts_f = [torch.from_numpy(wl.synthetic_batch(cfg, 3000 + 16 * rank + j)).pin_memory() for j in range(max(2, min(n_in, 4)))]
     for j in range(3):
         pipe.collect(pipe.submit(hosts_f[j % len(hosts_f)]))
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     prev = None
-    for i in range(args.steps):
+    f_steps = max(5, args.steps // 2)
+    for i in range(f_steps):
         tk = pipe.submit(hosts_f[i % len(hosts_f)])
         if prev is not None:
             pipe.collect(prev)
         prev = tk
     pipe.collect(prev)
     torch.cuda.synchronize()
-    e2e_f32_ms = 1000.0 * (time.perf_counter() - t2) / args.steps
-    pipe.engine.disable_u8_input()
-    pipe.engine.input_buffer.copy_(x_host)
+    e2e_f32_ms = 1000.0 * (time.perf_counter() - t2) / f_steps
     clocks = sampler.stop() if rank == 0 else None
-    n_found = int(hc.sum())
 
-    t = torch.tensor([dev_ms, t_e2e * 1000.0], dtype=torch.float64, device="cuda")
+    # ---- secondary device-resident figures --------------------------------------------------------
+    # (a) the round-1 method, for continuity: per-step event windows with a 256 MiB L2 flush between steps (N = 1 only)
+    flushed_ms = None
+    if world == 1:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        f_n = min(args.steps, 20)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(f_n)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(f_n)]
+        pipe.engine.bind_input(xs[0])
+        for i in range(f_n):
+            flush.zero_()
+            starts[i].record(stream)
+            pipe.step_device()
+            ends[i].record(stream)
+        torch.cuda.synchronize()
+        flushed_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / f_n
+        del flush
+    # (b) the precision-matched arithmetic (3xTF32: tf32 tensor cores, hi/lo split, ~fp32 products) beside the default
+    matched = None
+    if args.math != "tc_3xtf32":
+        pipe.engine.set_math(math_modes["tc_3xtf32"])
+        for j in range(n_in):
+            pipe.engine.bind_input(xs[j])
+            pipe.step_device()
+        m_steps = min(args.steps, 20)
+        m_ms = timed_steps(m_steps)
+        matched = {"math": "tc_3xtf32", "steps": m_steps, "ms": m_ms}
+        pipe.engine.set_math(math_modes[args.math])
+        for j in range(n_in):
+            pipe.engine.bind_input(xs[j])
+            pipe.step_device()
+        barrier()
+
+    vals = [dev_ms, t_e2e * 1000.0, matched["ms"] if matched else 0.0]
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, m_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peaks = load_peaks()
-        # dominant kernel, timed live with CUDA events between launches (k2y_net_profile), L2 flushed before each pass
+        # dominant launch, timed live with CUDA events between launches (k2y_net_profile); inputs rotate (cold in L2)
         acc = None
         reps = 5
-        for _ in range(reps):
-            flush.zero_()
-            prof = pipe.engine.profile(BATCH)
+        for r in range(reps):
+            pipe.engine.bind_input(xs[r % n_in])
+            prof = pipe.engine.profile(B)
             acc = prof if acc is None else [dict(a, ms=a["ms"] + b["ms"]) for a, b in zip(acc, prof)]
         for a in acc:
             a["ms"] /= reps
         net_ms = sum(a["ms"] for a in acc)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         det_ms = 0.0
-        for _ in range(reps):
-            heads = pipe.engine.run(BATCH)
+        for r in range(reps):
+            pipe.engine.bind_input(xs[r % n_in])
+            heads = pipe.engine.run(B)
             torch.cuda.synchronize()
             ev0.record(stream)
             pipe.detector.run(heads, pipe._img_hw)
             ev1.record(stream)
             torch.cuda.synchronize()
             det_ms += ev0.elapsed_time(ev1) / reps
-        top = max(acc, key=lambda a: a["ms"])
+        head_bytes = sum(int(t_.numel()) * 4 for t_ in pipe.engine.head_buffers)
+        det_entry = {"name": "detect (decode scan + per-class NMS)", "ms": det_ms, "flops": 0.0,
+                     "bytes": float(head_bytes + B * cfg["classes"] * (wl.MAX_PER_CLASS * 24 + 4))}
+        cands = acc + [det_entry]
+        top = max(cands, key=lambda a: a["ms"])
         tf32_note = "tensor peak = measured dense bf16 (cuBLAS); the bf16x3 split scheme issues 3 MMAs per useful MAC, so it tops out at 1/3 of it"
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", f"r02_traffic_{cfg['name']}.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get(top["name"])
@@ -356,41 +435,49 @@ def run_ours(args):
                     "issued_tflops": ach * passes, "issued_frac": ach * passes / peaks["bf16_tflops"]}
         else:
             roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9,
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "note": "algorithmic bytes = fp32 activations read once + written once"}
-        roof.update({"traffic": traffic, "peak_source": peaks["source"], "launch_ms": top["ms"], "share_of_net": top["ms"] / net_ms,
-                     "algorithmic_flops": top["flops"], "algorithmic_bytes": top["bytes"]})
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "note": "algorithmic bytes = fp32 activations read once + written once (detect: head tensors read once + records written)"}
+        roof.update({"traffic": traffic, "peak_source": peaks["source"], "launch_ms": top["ms"],
+                     "share_of_step": top["ms"] / (net_ms + det_ms), "algorithmic_flops": top["flops"], "algorithmic_bytes": top["bytes"]})
         roof["frac"] = roof["achieved"] / roof["peak"]
         layer_roof = sum(max(a["flops"] / (peaks["bf16_tflops"] * 1e12), a["bytes"] / (peaks["hbm_gbs"] * 1e9)) for a in acc) * 1e3
         ms_per_step = dev_ms / args.steps
-        value = world * BATCH * args.steps / (dev_ms * 1e-3)
-        cpu_ips, cores, sample = cpu_reference_throughput() if not args.no_cpu else (None, 0, "skipped")
+        value = world * B * args.steps / (dev_ms * 1e-3)
+        parity = parity_check(pipe, cfg, xs[0]) if not args.no_cpu else {"parity_checked": None, "note": "skipped (--no-cpu)"}
+        cpu = cpu_baseline(cfg) if (not args.no_cpu and world == 1) else {"value": None, "unit": "images/sec", "cores": 0, "kind": "port",
+                                                                          "sample": "skipped (--no-cpu or N > 1)"}
         out = {
-            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": cfg["metric"], "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32_simt": "f32", "tc_3xtf32": "tf32x3 (fp32 storage, fp32 accumulate)", "tc_tf32": "tf32",
                       "tc_bf16x3": "bf16x3 (fp32 storage split into hi+mid bf16 planes on chip, fp32 accumulate)"}[args.math],
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "math": args.math, "parallelism": f"image-shard x{world}",
-                       "l2": "flushed between steps (256 MiB write outside the per-step event window)",
-                       "detections_per_step": n_found, "obj_thresh": OBJ_THRESH, "iou_thresh": IOU_THRESH},
-            "e2e": {"value": world * BATCH * args.steps / (e2e_ms * 1e-3), "unit": "images/sec",
-                    "h2d_bytes_per_step": int(hosts[0].numel()), "d2h_bytes_per_step": int(hd.numel() * 4 + hc.numel() * 4),
+            "config": workload_config(cfg, world),
+            "arm": {"math": args.math,
+                    "parallelism": f"image-shard x{world}" + (", one ncclAllGather per step on a side stream" if world > 1 else ""),
+                    "l2": f"{n_in} distinct device-resident input batches in rotation ({n_in * in_bytes >> 20} MiB > 126 MiB L2), no flush inside the window",
+                    "detections_per_step": n_found},
+            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "images/sec",
+                    "h2d_bytes_per_step": int(hosts[0].numel()), "d2h_bytes_per_step": d2h_bytes,
                     "api": "DetectionPipeline.submit/collect (pinned host uint8 NHWC letterboxed RGB in, detection records out; "
-                           "img/max(img) on the GPU; H2D of step i+1 overlaps step i)",
-                    "inputs": "24 distinct pinned host batches in rotation (165 MB > L2)",
+                           "img/max(img) on the GPU; H2D of step i+1 overlaps step i, no staging copy)",
+                    "inputs": f"{n_host} distinct pinned host batches in rotation",
                     "single_call_ms": e2e_sync_ms,
-                    "f32_host_input": {"value": world * BATCH / (e2e_f32_ms * 1e-3), "h2d_bytes_per_step": int(x_host.numel() * 4)}},
+                    "f32_host_input": {"value": world * B / (e2e_f32_ms * 1e-3), "h2d_bytes_per_step": in_bytes}},
             "gpu_launches": pipe.launches_per_step() * args.steps,
             "clocks": clocks,
             "roofline": roof,
             "conv_roofline": {"layerwise_floor_ms": layer_roof, "net_ms_event_sum": net_ms, "frac": layer_roof / net_ms,
-                              "tensor_frac_whole_net": BATCH * FLOP_PER_IMAGE / (net_ms * 1e-3) / (peaks["bf16_tflops"] * 1e12),
+                              "tensor_frac_whole_net": B * cfg["gflop"] * 1e9 / (net_ms * 1e-3) / (peaks["bf16_tflops"] * 1e12),
                               "note": "sum over layers of max(FLOP/peak_bf16, fp32 act bytes/peak_hbm) / measured sum of launches"},
-            "cpu_baseline": {"value": cpu_ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample,
-                             "label": "TF-CPU stand-in (TF unavailable offline)"},
+            "cpu_baseline": cpu,
             "detect_ms": det_ms,
-            "top_launches": sorted(({"name": a["name"], "ms": round(a["ms"], 4)} for a in acc), key=lambda a: -a["ms"])[:6],
+            "ms_per_step_flushed": flushed_ms,
+            "precision_matched": ({"math": "tc_3xtf32", "value": world * B * matched["steps"] / (m_ms * 1e-3),
+                                   "ms_per_step": m_ms / matched["steps"], "unit": "images/sec"} if matched else None),
+            "top_launches": sorted(({"name": a["name"], "ms": round(a["ms"], 4)} for a in cands), key=lambda a: -a["ms"])[:6],
         }
+        out.update(parity)
         emit(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -403,10 +490,13 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", type=int, choices=sorted(wl.CONFIGS), default=2,
+                    help="BASELINE.json config: 2 yolo_mobilev1-0.75 (default, the headline), 3 tiny_yolo 416, 4 yolo_mobilev2, 5 Darknet-53 608")
     ap.add_argument("--math", choices=["fp32_simt", "tc_3xtf32", "tc_tf32", "tc_bf16x3"], default=os.environ.get("K2Y_BENCH_MATH", "tc_bf16x3"))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = wl.CONFIGS[args.config]
     # The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
     # version banner there on every rank): keep a private handle on the real stdout for the JSON line and point fd 1 at stderr.
     global _JSON_OUT
@@ -414,9 +504,9 @@ def main():
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
     else:
-        run_ours(args)
+        run_ours(args, cfg)
 
 
 if __name__ == "__main__":

@@ -90,6 +90,10 @@ int k2y_net_bind(k2y_net *net, void *workspace, size_t workspace_bytes, const fl
  * maximum, and the first convolution reads x = u8 / max through a 256-entry table (bit-identical to the float32 input the
  * reference feeds).  Pass NULL, NULL to return to the float32 input bound with k2y_net_bind. */
 int k2y_net_bind_u8(k2y_net *net, const unsigned char *x_u8_dev, int32_t *img_max_dev);
+/* Re-points the float32 input at another device buffer [max_batch,H,W,3] (workspace and heads stay as bound).  One CUDA
+ * graph is kept per (batch, input buffer), so alternating between two input buffers (H2D of batch i+1 while batch i runs)
+ * costs nothing after the first use of each.  k2y_net_bind_u8 behaves the same way for the uint8 input. */
+int k2y_net_bind_input(k2y_net *net, const float *x_dev);
 /* predict on bound device buffers (keras_inference.py:88), asynchronous on `stream`. */
 int k2y_net_run(k2y_net *net, int batch, void *stream);
 /* predict with HOST buffers: H2D of x, run, D2H of every head, stream-synchronised on return.
@@ -150,6 +154,31 @@ int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *heads_dev, i
                      const float *image_hw_dev, k2y_det *dets_dev, int32_t *counts_dev, void *workspace,
                      size_t workspace_bytes, void *stream);
 
+/* Same, with explicit per-image strides (in 32-bit words) of the two outputs, so that one image's records and counts can
+ * sit next to each other in a gather block: dets of image b start at (int32*)dets_dev + b*det_image_stride_words, counts at
+ * counts_dev + b*count_image_stride_words.  k2y_detect_keras == strides (C*max_per_class*6, C). */
+int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *const *heads_dev, int batch,
+                             const float *image_hw_dev, k2y_det *dets_dev, int32_t *counts_dev,
+                             long long det_image_stride_words, long long count_image_stride_words, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU collation: images shard across ranks (one process per GPU), and the one exchange on the path
+ * is ONE ncclAllGather of the fixed-size record blocks.  The reference is single-process (keras_inference.py:12-17), so
+ * this replaces nothing there — it is what makes `main()` scale over the 8 GPUs of a box.
+ *   k2y_comm_unique_id   rank 0: 128 bytes to hand to every rank (any transport)
+ *   k2y_comm_create      every rank: joins the communicator on `device`
+ *   k2y_allgather_detections  gather_dev = [world][bytes_per_rank]; this rank's block (filled by k2y_detect_keras_strided)
+ *                        lives at rank*bytes_per_rank; in place, asynchronous on `stream`; no-op for world == 1.
+ * NCCL is bound at run time (libnccl.so.2, or $K2Y_NCCL_LIB); K2Y_ERR_STATE if it cannot be found.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct k2y_comm k2y_comm;
+int k2y_comm_unique_id(unsigned char *id128);
+int k2y_comm_create(const unsigned char *id128, int world, int rank, int device, k2y_comm **out);
+int k2y_comm_destroy(k2y_comm *comm);
+int k2y_comm_info(const k2y_comm *comm, int *world, int *rank, int *nccl_version);
+int k2y_allgather_detections(k2y_comm *comm, void *gather_dev, size_t bytes_per_rank, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * REGION_C-dialect decode + NMS, batched on device  (region_layer.c:121-283 per layer).
  * in_dev: [batch][A][5+C][H][W] f32 planar.  Outputs (device): probs [batch][N][C+1] after NMS,
@@ -189,6 +218,13 @@ int k2y_correct_box(const float *xy_dev, const float *wh_dev, long long n_boxes,
 int k2y_nms_workspace_bytes(int n_boxes, int max_output_size, size_t *bytes);
 int k2y_nms_boxes(const float *boxes_dev, const float *scores_dev, int n_boxes, int max_output_size, float iou_threshold,
                   int32_t *indices_dev, int32_t *count_dev, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Parity hook: the float32 exponential each decode dialect is pinned to, element-wise on device arrays.
+ *   mode 0  correctly rounded exp (KERAS dialect: tools/utils.py:545-546 / keras_inference.py:101 evaluate exp and sigmoid inside
+ *           TensorFlow, whose last-bit behaviour is not reproducible; this build and oracle/decode_ref.py define it as the
+ *           correctly rounded value so that score order and NMS survivor sets are a function of the head tensors alone)
+ *   mode 1  glibc's expf algorithm bit for bit (REGION_C dialect: region_layer.c:75,104 call libm's expf) */
+int k2y_expf_eval(int mode, const float *x_dev, float *y_dev, long long n, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-processing: aspect-preserving letterbox of ONE uint8 HWC RGB image on the device

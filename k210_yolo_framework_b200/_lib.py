@@ -68,6 +68,7 @@ _SIGNATURES = {
     "k2y_net_workspace_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),
     "k2y_net_bind": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_void_p), c_int]),
     "k2y_net_bind_u8": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "k2y_net_bind_input": (c_int, [c_void_p, c_void_p]),
     "k2y_net_run": (c_int, [c_void_p, c_int, c_void_p]),
     "k2y_net_predict_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_void_p), c_void_p]),
     "k2y_net_launches_per_run": (c_int, [c_void_p, POINTER(c_int)]),
@@ -82,6 +83,13 @@ _SIGNATURES = {
     "k2y_detect_workspace_bytes": (c_int, [POINTER(DetectCfg), c_int, POINTER(c_size_t)]),
     "k2y_detect_keras": (c_int, [POINTER(DetectCfg), POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    "k2y_detect_keras_strided": (c_int, [POINTER(DetectCfg), POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p,
+                                         ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_size_t, c_void_p]),
+    "k2y_comm_unique_id": (c_int, [c_void_p]),
+    "k2y_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "k2y_comm_destroy": (c_int, [c_void_p]),
+    "k2y_comm_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "k2y_allgather_detections": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "k2y_region_workspace_bytes": (c_int, [POINTER(RegionCfg), c_int, POINTER(c_size_t)]),
     "k2y_region_run": (c_int, [POINTER(RegionCfg), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
@@ -90,6 +98,7 @@ _SIGNATURES = {
     "k2y_correct_box": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
     "k2y_nms_workspace_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "k2y_nms_boxes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "k2y_expf_eval": (c_int, [c_int, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
     "k2y_letterbox_u8": (c_int, [c_void_p, c_int, c_int, POINTER(ctypes.c_double), c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 # include/region_layer.h (ABI-compatible firmware API)

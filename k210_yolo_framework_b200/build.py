@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libk210yolo_b200.so")
-SOURCES = ["conv_simt.cu", "gemm_tc.cu", "detect.cu", "net.cu", "region_layer_abi.cu", "preprocess.cu"]
+SOURCES = ["conv_simt.cu", "gemm_tc.cu", "detect.cu", "net.cu", "region_layer_abi.cu", "preprocess.cu", "comm.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -29,7 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -46,6 +46,10 @@ struct ConvArgs {
     const int *img_max = nullptr;
     // host copies of w / scale / shift (first conv: passed to the kernel BY VALUE, i.e. through the constant bank)
     const float *w_host = nullptr, *scale_host = nullptr, *shift_host = nullptr;
+    // caller-owned scratch for split-K partials (one per net, so nets on different streams never share it); null = the
+    // per-device default of the single-layer test hook
+    float *tc_scratch = nullptr;
+    size_t tc_scratch_bytes = 0;
 };
 
 struct DwArgs {

@@ -1,15 +1,23 @@
 // Fused decode + per-class greedy NMS, both dialects of the reference:
 //   KERAS    keras_inference.py:94-135 (+ tools/utils.py:524-547, keras_inference.py:32-72)
 //   REGION_C yolo3_frame_test_public/region_layer.c:121-283
-// KERAS: one warp per (image, class): scan of the head tensors (score = sigmoid(cls) * sigmoid(conf)) with
-// ballot-compaction of the candidates in index order, register-resident bitonic sort on (score desc, index asc)
-// keys, then greedy IoU suppression resolved 32 candidates at a time (kept boxes and the chunk's candidates cached
-// (min,max)-normalised in shared memory, intra-chunk suppression as bitmasks).  REGION_C: one CTA per image (softmax +
-// decode by all threads, then one warp per class).  Final records are written contiguously per (image, class).
+// KERAS, two kernels:
+//   detect_scan_kernel  CTA = 64-box slab of one image.  The slab's records ([box][5+C] floats, contiguous in the NHWC head)
+//                       are staged in shared memory with coalesced loads, so every head value is read from HBM exactly once;
+//                       sigmoid(conf) is evaluated once per box, every box is decoded once (tf_xywh_to_all + correct_box)
+//                       into a per-image box table, and every (box, class) with score >= obj_thresh appends its sort key
+//                       (score bits << 32 | ~index) to the class's candidate list.
+//   detect_nms_kernel   CTA = one (image, class): CTA-wide bitonic sort of the keys in shared memory, candidate boxes
+//                       gathered from the box table, then the greedy selection as <= max_per_class rounds of
+//                       "first candidate still alive -> keep -> every thread tests its candidates against it".
+// REGION_C: one CTA per image (softmax + decode by all threads, then one warp per class).
 //
-// Arithmetic is float32 in the reference's operation order with explicit round-to-nearest
-// intrinsics where FMA contraction would change a rounding, so survivor sets are bit-identical to
-// the oracle's whenever the transcendental results (expf) agree.
+// Arithmetic is float32 in the reference's operation order with explicit round-to-nearest intrinsics where FMA
+// contraction would change a rounding.  exp() is DEFINED, for the KERAS dialect, as the correctly rounded float32
+// exponential (computed in double and rounded once; oracle/decode_ref.py does the same), so scores, their order and
+// therefore the survivor sets are bit-identical to the oracle's on identical head tensors.  The REGION_C dialect calls
+// glibc's expf in the reference; expf_glibc() below restates that algorithm (table + cubic in double) bit for bit.
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -20,11 +28,43 @@ namespace k2y {
 namespace {
 
 constexpr int DET_THREADS = 1024;
-constexpr int DET_WARPS = 4;          // classes per CTA in the KERAS kernel
-constexpr int DET_SMEM_KEYS = 4096;   // per-warp key capacity in shared memory (32 KB)
 constexpr unsigned FULL = 0xffffffffu;
 
-__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// correctly rounded float32 exp: double-precision exp (<= 1 ulp of double) rounded once to float
+__device__ __forceinline__ float exp_cr(float x) { return __double2float_rn(exp((double)x)); }
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, exp_cr(-x))); }
+
+// glibc >= 2.28 expf (sysdeps/ieee754/flt-32/e_expf.c, EXP2F_TABLE_BITS = 5): exp(x) = 2^(k/32) * 2^(r/32) with
+// k = round(x * 32/ln2), the second factor a cubic in r, all in double, one final rounding to float.  The x86-64 build
+// selects the FMA variant on every CPU of this decade, hence the explicit fma()s.  Overflow/underflow limits as glibc's.
+__constant__ unsigned long long EXP2F_TAB[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+};
+__device__ __forceinline__ float expf_glibc(float x) {
+    if (!(x == x)) return x + x;
+    if (x > 88.72283172607421875f) return __int_as_float(0x7f800000);   // 0x1.62e42ep6f
+    if (x < -103.97207641601562500f) return 0.0f;                       // -0x1.9fe368p6f
+    const double z = __dmul_rn(0x1.71547652b82fep+5, (double)x);         // 32/ln2
+    double kd = __dadd_rn(z, 6755399441055744.0);                        // + 0x1.8p52: round to nearest integer
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, 6755399441055744.0);
+    const double r = __dsub_rn(z, kd);
+    const unsigned long long t = EXP2F_TAB[ki & 31ull] + (ki << 47);
+    const double s = __longlong_as_double((long long)t);
+    const double zz = __fma_rn(0x1.c6af84b912394p-20, r, 0x1.ebfce50fac4f3p-13);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(0x1.62e42ff0c52d6p-6, r, 1.0);
+    y = __fma_rn(zz, r2, y);
+    return __double2float_rn(__dmul_rn(y, s));
+}
+__device__ __forceinline__ float sigmoidf_glibc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc(-x))); }
 
 __device__ __forceinline__ unsigned long long pack_key(float score, int idx) {
     // scores are > 0 here, so the IEEE bit pattern is monotonic; larger key == earlier in the order
@@ -49,53 +89,6 @@ __device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long 
     return key;
 }
 
-// Bitonic sort (descending) of 32*R keys held R per lane, element e = r*32 + lane.  Exchanges at distance >= 32 are
-// register-to-register inside a lane, shorter ones are warp shuffles; everything is unrolled, so the keys never leave
-// the register file (the in-memory version below cost ~100 cycles per compare-exchange on the critical path).
-template <int R>
-__device__ __forceinline__ void warp_sort_desc_regs(unsigned long long (&key)[R], int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32 * R; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int rj = j >> 5;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if ((r & rj) == 0) {
-                        const bool desc = ((r * 32) & k) == 0;  // k >= 64 here: decided by the register index alone
-                        const unsigned long long a = key[r], b = key[r ^ rj];
-                        const unsigned long long mx = a > b ? a : b, mn = a > b ? b : a;
-                        key[r] = desc ? mx : mn;
-                        key[r ^ rj] = desc ? mn : mx;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const unsigned long long other = __shfl_xor_sync(FULL, key[r], j);
-                    const bool desc = (((r * 32 + lane) & k) == 0);
-                    const bool lower = ((lane & j) == 0);
-                    const bool take_max = (desc == lower);
-                    key[r] = take_max ? (key[r] > other ? key[r] : other) : (key[r] < other ? key[r] : other);
-                }
-            }
-        }
-    }
-}
-
-template <int R>
-__device__ __forceinline__ void warp_sort_desc_via_regs(unsigned long long *keys, int n, int lane) {
-    unsigned long long k[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) k[r] = (r * 32 + lane < n) ? keys[r * 32 + lane] : 0ull;
-    warp_sort_desc_regs<R>(k, lane);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < R; ++r) keys[r * 32 + lane] = k[r];
-    __syncwarp();
-}
-
 // Bitonic sort (descending) of P (power of two) keys in memory by one warp.
 __device__ __forceinline__ void warp_sort_desc_mem(unsigned long long *keys, int P, int lane) {
     for (int k = 2; k <= P; k <<= 1) {
@@ -117,31 +110,10 @@ __device__ __forceinline__ void warp_sort_desc_mem(unsigned long long *keys, int
 }
 
 // tf.image.non_max_suppression's test `IoU(a, b) > thr` on (ymin,xmin,ymax,xmax) boxes (zero-area boxes -> IoU 0), without
-// the division in the common case: inter/uni > thr  <=>  inter > thr*uni (uni > 0).
-// The product form is only trusted outside a 1e-6 relative margin (>> the 3 roundings involved); inside it the
-// exact IEEE division decides, so the boolean is bit-identical to the reference's `iou > iou_threshold`.
-__device__ __forceinline__ bool iou_yxyx_gt(const float4 a, const float4 b, float thr) {
-    const float ymin_a = fminf(a.x, a.z), ymax_a = fmaxf(a.x, a.z);
-    const float xmin_a = fminf(a.y, a.w), xmax_a = fmaxf(a.y, a.w);
-    const float ymin_b = fminf(b.x, b.z), ymax_b = fmaxf(b.x, b.z);
-    const float xmin_b = fminf(b.y, b.w), xmax_b = fmaxf(b.y, b.w);
-    const float area_a = __fmul_rn(__fsub_rn(ymax_a, ymin_a), __fsub_rn(xmax_a, xmin_a));
-    const float area_b = __fmul_rn(__fsub_rn(ymax_b, ymin_b), __fsub_rn(xmax_b, xmin_b));
-    if (area_a <= 0.f || area_b <= 0.f) return 0.f > thr;
-    const float iy = fmaxf(__fsub_rn(fminf(ymax_a, ymax_b), fmaxf(ymin_a, ymin_b)), 0.f);
-    const float ix = fmaxf(__fsub_rn(fminf(xmax_a, xmax_b), fmaxf(xmin_a, xmin_b)), 0.f);
-    const float inter = __fmul_rn(iy, ix);
-    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-    if (thr >= 0.f && uni > 0.f) {
-        const float t = __fmul_rn(thr, uni);
-        if (inter > __fmul_rn(t, 1.000001f)) return true;
-        if (inter < __fmul_rn(t, 0.999999f)) return false;
-    }
-    return __fdiv_rn(inter, uni) > thr;
-}
-
-// Same predicate on boxes already (min,max)-normalised with their areas cached (computed exactly as above, once per
-// box instead of once per pair).
+// the division in the common case: inter/uni > thr  <=>  inter > thr*uni (uni > 0).  The product form is only trusted
+// outside a 1e-6 relative margin (>> the 3 roundings involved); inside it the exact IEEE division decides, so the
+// boolean is bit-identical to the reference's `iou > iou_threshold`.  Boxes are (min,max)-normalised with their areas
+// cached (once per box instead of once per pair).
 __device__ __forceinline__ float4 norm_box(const float4 a, float &area) {
     float4 n;
     n.x = fminf(a.x, a.z);
@@ -190,13 +162,18 @@ struct KerasParams {
     float anchors[48];
     float in_h, in_w;
     float obj, iou;
+    float logit_min;                  // a logit below this cannot give a sigmoid >= obj (with a wide margin); -inf = no shortcut
     int maxk;
     const float *image_hw;
     k2y_det *dets;
     int *counts;
-    unsigned long long *keys_global;  // [B][C][P] — only used when P does not fit shared memory
-    int keys_in_smem;
-    long long *trace;                 // optional [B][C][4]: cycles of scan / sort / nms and the candidate count (K2Y_DET_TRACE=1)
+    long long det_stride, cnt_stride;  // per-image strides of dets / counts in 32-bit words (dense: C*maxk*6 and C)
+    // workspace
+    float4 *boxes;                    // [B][nbox] decoded (ymin,xmin,ymax,xmax) of every box
+    unsigned long long *keys;         // [B][C][P] candidate sort keys
+    int *ncand;                       // [B][C] candidates per (image, class); zeroed before the scan
+    unsigned *alive;                  // [B][C][P/32] (only used when a class has more candidates than fit shared memory)
+    int cap, pcap;                    // candidates the NMS kernel can hold in shared memory; pcap = next power of two (sort extent)
 };
 
 // Collects the candidates of one class (score passes `pred`) in index order, sorts them.
@@ -232,28 +209,34 @@ struct BoxXform {  // correct_box constants of one image (keras_inference.py:53-
     float img_h, img_w, off_y, off_x, sc_y, sc_x;
 };
 
-__device__ __forceinline__ const float *box_entry(const KerasParams &p, int b, int box, int &l, int &a, int &col, int &row) {
-    l = 0;
+__device__ __forceinline__ BoxXform make_xform(const KerasParams &p, int b) {
+    BoxXform x;
+    x.img_h = p.image_hw[2 * b];
+    x.img_w = p.image_hw[2 * b + 1];
+    const float r = fminf(__fdiv_rn(p.in_h, x.img_h), __fdiv_rn(p.in_w, x.img_w));
+    const float new_h = rintf(__fmul_rn(x.img_h, r)), new_w = rintf(__fmul_rn(x.img_w, r));
+    x.off_y = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_h, new_h), 2.0f), p.in_h);
+    x.off_x = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_w, new_w), 2.0f), p.in_w);
+    x.sc_y = __fdiv_rn(p.in_h, new_h);
+    x.sc_x = __fdiv_rn(p.in_w, new_w);
+    return x;
+}
+
+// tf_xywh_to_all (tools/utils.py:545-546) + correct_box (keras_inference.py:59-71) for one box; e = its (tx,ty,tw,th,..) record.
+__device__ __forceinline__ float4 decode_box(const KerasParams &p, const BoxXform &x, int box, const float *e) {
+    int l = 0;
     if (p.n_layers > 1 && box >= p.loff[1]) l = 1;
     if (p.n_layers > 2 && box >= p.loff[2]) l = 2;
     const int local = box - p.loff[l];
-    a = local % p.A;
+    const int a = local % p.A;
     const int cell = local / p.A;
     const int W = p.lw[l];
-    col = cell % W;
-    row = cell / W;
-    return p.heads[l] + ((size_t)((size_t)b * p.lh[l] * W + cell) * p.A + a) * (5 + p.C);
-}
-
-// tf_xywh_to_all (tools/utils.py:545-546) + correct_box (keras_inference.py:59-71) for one box.
-__device__ __forceinline__ float4 decode_box(const KerasParams &p, const BoxXform &x, int b, int box) {
-    int l, a, col, row;
-    const float *e = box_entry(p, b, box, l, a, col, row);
-    const float tx = __ldg(e), ty = __ldg(e + 1), tw = __ldg(e + 2), th = __ldg(e + 3);
-    const float bx = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)p.lw[l]);
+    const int col = cell % W, row = cell / W;
+    const float tx = e[0], ty = e[1], tw = e[2], th = e[3];
+    const float bx = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)W);
     const float by = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)p.lh[l]);
-    const float bw = __fmul_rn(expf(tw), p.anchors[(l * p.A + a) * 2]);
-    const float bh = __fmul_rn(expf(th), p.anchors[(l * p.A + a) * 2 + 1]);
+    const float bw = __fmul_rn(exp_cr(tw), p.anchors[(l * p.A + a) * 2]);
+    const float bh = __fmul_rn(exp_cr(th), p.anchors[(l * p.A + a) * 2 + 1]);
     const float cy = __fmul_rn(__fsub_rn(by, x.off_y), x.sc_y), cx = __fmul_rn(__fsub_rn(bx, x.off_x), x.sc_x);
     const float hh2 = __fdiv_rn(__fmul_rn(bh, x.sc_y), 2.0f), ww2 = __fdiv_rn(__fmul_rn(bw, x.sc_x), 2.0f);
     float4 r;
@@ -264,195 +247,219 @@ __device__ __forceinline__ float4 decode_box(const KerasParams &p, const BoxXfor
     return r;
 }
 
-// grid = (ceil(C / warps), B): one warp owns one (image, class).  It scans the head tensors for its class
-// (score = sigmoid(cls) * sigmoid(conf)), compacts the candidates in index order into sort keys, sorts them, decodes
-// the candidate boxes 32 at a time (one per lane) and runs the greedy suppression with shuffles.
-__global__ void __launch_bounds__(DET_WARPS * 32) detect_keras_kernel(const KerasParams p) {
+// ---- pass 1: scan.  grid = (ceil(nbox / 64), B) ----------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_BOXES = 64;
+
+__global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasParams p) {
+    extern __shared__ __align__(16) float s_scan[];  // [SCAN_BOXES][E] records, then [SCAN_BOXES] sigmoid(conf)
     pdl_trigger();
-    pdl_wait();
-    extern __shared__ __align__(16) unsigned long long smem_keys[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
-    const int c = blockIdx.x * DET_WARPS + warp;
-    if (c >= p.C) return;
-    unsigned long long *keys = p.keys_in_smem ? smem_keys + (size_t)warp * p.P : p.keys_global + ((size_t)b * p.C + c) * p.P;
-
-    BoxXform x;
-    x.img_h = p.image_hw[2 * b];
-    x.img_w = p.image_hw[2 * b + 1];
-    const float r = fminf(__fdiv_rn(p.in_h, x.img_h), __fdiv_rn(p.in_w, x.img_w));
-    const float new_h = rintf(__fmul_rn(x.img_h, r)), new_w = rintf(__fmul_rn(x.img_w, r));
-    x.off_y = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_h, new_h), 2.0f), p.in_h);
-    x.off_x = __fdiv_rn(__fdiv_rn(__fsub_rn(p.in_w, new_w), 2.0f), p.in_w);
-    x.sc_y = __fdiv_rn(p.in_h, new_h);
-    x.sc_x = __fdiv_rn(p.in_w, new_w);
-
-    // ---- scan: candidates of class c in index order (4 x 32 boxes per step so that the loads overlap) ----
-    const long long tc0 = p.trace ? clock64() : 0;
-    int n = 0;
-    for (int base = 0; base < p.nbox; base += 128) {
-        float lc[4], lk[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int box = base + u * 32 + lane;
-            lc[u] = 0.f;
-            lk[u] = 0.f;
-            if (box < p.nbox) {
-                // entry pointer needs no (row, col, anchor) split: boxes of a layer are contiguous [cell][anchor] records
-                int l = 0;
-                if (p.n_layers > 1 && box >= p.loff[1]) l = 1;
-                if (p.n_layers > 2 && box >= p.loff[2]) l = 2;
-                const float *e = p.heads[l] + ((size_t)b * (p.loff[l + 1] - p.loff[l]) + (box - p.loff[l])) * (5 + p.C);
-                lc[u] = __ldg(e + 4);
-                lk[u] = __ldg(e + 5 + c);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int box = base + u * 32 + lane;
-            bool pass = false;
-            float s = 0.f;
-            if (box < p.nbox) {
-                s = __fmul_rn(sigmoidf_ref(lk[u]), sigmoidf_ref(lc[u]));
-                pass = s >= p.obj;
-            }
-            const unsigned m = __ballot_sync(FULL, pass);
-            if (pass) keys[n + __popc(m & ((1u << lane) - 1u))] = pack_key(s, box);
-            n += __popc(m);
+    const int b = blockIdx.y, box0 = blockIdx.x * SCAN_BOXES, tid = threadIdx.x;
+    const int nb = min(SCAN_BOXES, p.nbox - box0);
+    const int E = 5 + p.C;
+    float *s_rec = s_scan, *s_conf = s_scan + SCAN_BOXES * E;
+    pdl_wait();  // the heads belong to the previous kernel
+    // the boxes of a layer are contiguous [cell][anchor] records of the NHWC head: a slab is one run per layer it touches
+    for (int l = 0; l < p.n_layers; ++l) {
+        const int lo = max(box0, p.loff[l]), hi = min(box0 + nb, p.loff[l + 1]);
+        if (lo >= hi) continue;
+        const float *src = p.heads[l] + ((size_t)b * (p.loff[l + 1] - p.loff[l]) + (lo - p.loff[l])) * E;
+        float *dst = s_rec + (lo - box0) * E;
+        const int cnt = (hi - lo) * E;
+        for (int i = tid; i < cnt; i += SCAN_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (tid < nb) {
+        // sigmoid(conf) once per box; score = sigmoid(cls) * sigmoid(conf) <= sigmoid(conf), so a box whose objectness is
+        // below the threshold has no candidate in any class (0 marks it: obj > 0 whenever the shortcut is on)
+        const float t = s_rec[tid * E + 4];
+        s_conf[tid] = (t < p.logit_min) ? 0.f : sigmoidf_ref(t);
+    } else if (tid >= SCAN_BOXES && tid < SCAN_BOXES + nb) {
+        const int i = tid - SCAN_BOXES;
+        const BoxXform x = make_xform(p, b);
+        p.boxes[(size_t)b * p.nbox + box0 + i] = decode_box(p, x, box0 + i, s_rec + i * E);
+    }
+    __syncthreads();
+    const bool shortcut = p.logit_min > -__int_as_float(0x7f800000);
+    for (int it = tid; it < nb * p.C; it += SCAN_THREADS) {
+        const int i = it / p.C, c = it - i * p.C;
+        const float sc = s_conf[i];
+        if (shortcut && !(sc >= p.obj)) continue;
+        const float t = s_rec[i * E + 5 + c];
+        if (t < p.logit_min) continue;
+        const float s = __fmul_rn(sigmoidf_ref(t), sc);
+        if (s >= p.obj) {
+            const int pos = atomicAdd(p.ncand + b * p.C + c, 1);
+            p.keys[((size_t)b * p.C + c) * p.P + pos] = pack_key(s, box0 + i);
         }
     }
-    __syncwarp();
-    const long long tc1 = p.trace ? clock64() : 0;
-    unsigned long long rkey = 0ull;
-    if (n <= 32) {
-        if (lane < n) rkey = keys[lane];
-        rkey = warp_sort_desc(rkey, lane);
-    } else if (n <= 64) {
-        warp_sort_desc_via_regs<2>(keys, n, lane);
-    } else if (n <= 128) {
-        warp_sort_desc_via_regs<4>(keys, n, lane);
-    } else if (n <= 256) {
-        warp_sort_desc_via_regs<8>(keys, n, lane);
-    } else if (n <= 512) {
-        warp_sort_desc_via_regs<16>(keys, n, lane);
-    } else if (n <= 1024 && p.P >= 1024) {
-        warp_sort_desc_via_regs<32>(keys, n, lane);
-    } else {
-        int P = 64;
-        while (P < n) P <<= 1;
-        for (int i = n + lane; i < P; i += 32) keys[i] = 0ull;
-        __syncwarp();
-        warp_sort_desc_mem(keys, P, lane);
-    }
+}
 
-    const long long tc2 = p.trace ? clock64() : 0;
-    // ---- greedy NMS over the sorted candidates, 32 at a time ----
-    // Per chunk: (a) every lane tests ITS candidate against the boxes kept so far, (b) every lane computes the bitmask
-    // of later candidates of the chunk its box would suppress, (c) a short warp-uniform scan over the chunk resolves
-    // the greedy order from the masks.  The IoU work is thereby done 32-wide instead of one candidate at a time;
-    // the result is exactly the sequential algorithm's (a candidate is kept iff no earlier KEPT box overlaps it).
-    k2y_det *out = p.dets + ((size_t)b * p.C + c) * p.maxk;
-    __shared__ float4 s_kbox[DET_WARPS][32], s_cbox[DET_WARPS][32];   // kept / candidate boxes, (min,max)-normalised
-    __shared__ float s_karea[DET_WARPS][32], s_carea[DET_WARPS][32];
-    __shared__ float4 s_orig[DET_WARPS][32];            // candidate boxes as decoded (the records keep these)
-    __shared__ unsigned long long s_key[DET_WARPS][32];
-    __shared__ unsigned s_mask[DET_WARPS][32];
-    float4 *kbox = s_kbox[warp], *cbox = s_cbox[warp];
-    float *karea = s_karea[warp], *carea = s_carea[warp];
-    int nsel = 0;
-    long long t_dec = 0, t_a = 0, t_b = 0, t_c = 0;
-    for (int base = 0; base < n && nsel < p.maxk; base += 32) {
-        const long long q0 = p.trace ? clock64() : 0;
-        const int i = base + lane;
-        const unsigned long long mykey = (n <= 32) ? rkey : (i < n ? keys[i] : 0ull);
-        const int cnt = min(32, n - base);
-        float4 cand = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) cand = decode_box(p, x, b, key_index(mykey));
-        float my_area;
-        const float4 my = norm_box(cand, my_area);
-        cbox[lane] = my;
-        carea[lane] = my_area;
-        __syncwarp();
-        const long long q1 = p.trace ? clock64() : 0;
-        // (a) against the kept set: two kept boxes per step (independent chains), stop as soon as the chunk is dead
-        bool dead = lane >= cnt;
-        const int nreg = min(nsel, 32);
-        for (int s2 = 0; s2 < nreg; s2 += 4) {  // four independent IoU chains per step
-            if (__ballot_sync(FULL, !dead) == 0u) break;
-            bool hit = false;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int si = s2 + u < nreg ? s2 + u : s2;
-                hit |= iou_norm_gt(my, my_area, kbox[si], karea[si], p.iou);
-            }
-            dead = dead || hit;
-        }
-        for (int s2 = 32; s2 < nsel; ++s2) {  // only when max_per_class > 32
-            const k2y_det d = out[s2];
-            if (!dead && iou_yxyx_gt(cand, make_float4(d.ymin, d.xmin, d.ymax, d.xmax), p.iou)) dead = true;
-        }
-        const long long q2 = p.trace ? clock64() : 0;
-        // (b) suppression masks inside the chunk — only candidates that survived (a) can suppress anything
-        const unsigned alive = ~__ballot_sync(FULL, dead);
-        unsigned mask = 0u;
-        for (unsigned mm = alive; mm;) {
-            const int j0 = __ffs(mm) - 1;
-            mm &= mm - 1u;
-            const int j1 = mm ? __ffs(mm) - 1 : j0;
-            mm &= mm - 1u;
-            const bool h0 = iou_norm_gt(cbox[j0], carea[j0], my, my_area, p.iou);
-            const bool h1 = iou_norm_gt(cbox[j1], carea[j1], my, my_area, p.iou);
-            if (!dead) {
-                if (j0 > lane && h0) mask |= 1u << j0;
-                if (j1 > lane && h1) mask |= 1u << j1;
-            }
-        }
-        s_mask[warp][lane] = mask;
-        s_key[warp][lane] = mykey;
-        s_orig[warp][lane] = cand;
-        __syncwarp();
-        const long long q3 = p.trace ? clock64() : 0;
-        // (c) resolve in score order — a short warp-uniform scan; lane 0 records the survivors
-        unsigned remv = ~alive;
-        for (unsigned mm = alive; mm && nsel < p.maxk; mm &= mm - 1u) {
-            const int j = __ffs(mm) - 1;
-            if ((remv >> j) & 1u) continue;
-            remv |= s_mask[warp][j];
-            if (lane == 0) {
-                if (nsel < 32) {
-                    kbox[nsel] = cbox[j];
-                    karea[nsel] = carea[j];
+// ---- pass 2: sort + greedy NMS.  grid = (C, B), one CTA per (image, class) --------------------------------------------
+constexpr int NMS_THREADS = 128;
+constexpr int NMS_WARPS = NMS_THREADS / 32;
+
+// CTA-wide bitonic sort (descending) of P (power of two >= 64) keys in shared or global memory.
+__device__ __forceinline__ void cta_sort_desc(unsigned long long *keys, int P, int tid) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += NMS_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // t with a 0 inserted at bit log2(j)
+                const int ixj = i | j;
+                const unsigned long long a = keys[i], b = keys[ixj];
+                const bool desc = ((i & k) == 0);
+                if (desc ? (a < b) : (a > b)) {
+                    keys[i] = b;
+                    keys[ixj] = a;
                 }
-                const float4 kb = s_orig[warp][j];
-                const unsigned long long key = s_key[warp][j];
-                k2y_det d;
-                d.ymin = kb.x;
-                d.xmin = kb.y;
-                d.ymax = kb.z;
-                d.xmax = kb.w;
-                d.score = key_score(key);
-                d.index = key_index(key);
-                out[nsel] = d;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long long key, const float4 kb) {
+    k2y_det d;
+    d.ymin = kb.x;
+    d.xmin = kb.y;
+    d.ymax = kb.z;
+    d.xmax = kb.w;
+    d.score = key_score(key);
+    d.index = key_index(key);
+    out[slot] = d;
+}
+
+__global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasParams p) {
+    extern __shared__ __align__(16) unsigned char s_nms[];
+    __shared__ int s_min[2][NMS_WARPS];
+    pdl_trigger();
+    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();
+    const int n = p.ncand[b * p.C + c];
+    k2y_det *out = reinterpret_cast<k2y_det *>(reinterpret_cast<int *>(p.dets) + (size_t)b * p.det_stride) + (size_t)c * p.maxk;
+    int *count_out = p.counts + (size_t)b * p.cnt_stride + c;
+    if (n == 0) {
+        if (tid == 0) *count_out = 0;
+        return;
+    }
+    unsigned long long *gkeys = p.keys + ((size_t)b * p.C + c) * p.P;
+    const float4 *gboxes = p.boxes + (size_t)b * p.nbox;
+
+    if (n <= 32) {
+        // ---- a handful of candidates (every real image): one warp, keys and boxes in registers ----
+        if (warp != 0) return;
+        unsigned long long key = lane < n ? gkeys[lane] : 0ull;
+        key = warp_sort_desc(key, lane);
+        float4 orig = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < n) orig = gboxes[key_index(key)];
+        float area;
+        const float4 nb4 = norm_box(orig, area);
+        bool alive = lane < n;
+        int nsel = 0;
+        for (int i = 0; i < n && nsel < p.maxk; ++i) {
+            if (!((__ballot_sync(FULL, alive) >> i) & 1u)) continue;
+            float4 kb;
+            kb.x = __shfl_sync(FULL, nb4.x, i);
+            kb.y = __shfl_sync(FULL, nb4.y, i);
+            kb.z = __shfl_sync(FULL, nb4.z, i);
+            kb.w = __shfl_sync(FULL, nb4.w, i);
+            const float ka = __shfl_sync(FULL, area, i);
+            if (lane == i) {
+                write_det(out, nsel, key, orig);
+                alive = false;
+            } else if (lane > i && alive && iou_norm_gt(kb, ka, nb4, area, p.iou)) {
+                alive = false;
             }
             ++nsel;
         }
-        __syncwarp();
-        if (p.trace) {
-            const long long q4 = clock64();
-            t_dec += q1 - q0;
-            t_a += q2 - q1;
-            t_b += q3 - q2;
-            t_c += q4 - q3;
+        if (lane == 0) *count_out = nsel;
+        return;
+    }
+
+    int P2 = 64;
+    while (P2 < n) P2 <<= 1;
+    const bool in_smem = n <= p.cap;
+    unsigned long long *keys = in_smem ? reinterpret_cast<unsigned long long *>(s_nms) : gkeys;
+    float4 *s_box = reinterpret_cast<float4 *>(s_nms + (size_t)p.pcap * 8);   // (min,max)-normalised candidate boxes
+    float *s_area = reinterpret_cast<float *>(s_nms + (size_t)p.pcap * 8 + (size_t)p.cap * 16);
+    if (in_smem) {
+        for (int i = tid; i < P2; i += NMS_THREADS) keys[i] = i < n ? gkeys[i] : 0ull;
+    } else {
+        for (int i = n + tid; i < P2; i += NMS_THREADS) keys[i] = 0ull;
+    }
+    __syncthreads();
+    cta_sort_desc(keys, P2, tid);
+    // candidate `pos` (sorted order) belongs to thread pos % 128; its liveness is bit (pos / 128) % 32 of mask word (pos / 128) / 32
+    unsigned *alive_g = p.alive + ((size_t)b * p.C + c) * (size_t)(p.P >> 5);
+    const int slots = (n - tid + NMS_THREADS - 1) / NMS_THREADS;  // candidates this thread owns (n > 32 >= ... may be 0 for high tids)
+    unsigned mask0 = 0u;                                            // smem path: <= 32 slots per thread (cap <= 4096)
+    if (in_smem) {
+        for (int q = 0; q < slots; ++q) {
+            const int pos = tid + q * NMS_THREADS;
+            float ar;
+            s_box[pos] = norm_box(gboxes[key_index(keys[pos])], ar);
+            s_area[pos] = ar;
+        }
+        mask0 = slots >= 32 ? 0xffffffffu : ((1u << slots) - 1u);
+    } else {
+        for (int w = 0; w * 32 < slots; ++w) {
+            const int left = slots - w * 32;
+            alive_g[(size_t)w * NMS_THREADS + tid] = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
         }
     }
-    if (lane == 0) p.counts[b * p.C + c] = nsel;
-    if (p.trace && lane == 0) {
-        long long *o = p.trace + ((size_t)b * p.C + c) * 4;
-        o[0] = tc1 - tc0;
-        o[1] = tc2 - tc1;
-        o[2] = clock64() - tc2;
-        o[3] = n;
+    __syncthreads();
+    int nsel = 0, par = 0;
+    int first_w = 0;  // global path: first mask word of this thread that may still be non-zero
+    while (nsel < p.maxk) {
+        int my = 0x7fffffff;
+        if (in_smem) {
+            if (mask0) my = tid + (__ffs(mask0) - 1) * NMS_THREADS;
+        } else {
+            while (first_w * 32 < slots && alive_g[(size_t)first_w * NMS_THREADS + tid] == 0u) ++first_w;
+            if (first_w * 32 < slots) my = tid + (first_w * 32 + __ffs(alive_g[(size_t)first_w * NMS_THREADS + tid]) - 1) * NMS_THREADS;
+        }
+        const int wmin = __reduce_min_sync(FULL, my);
+        if (lane == 0) s_min[par][warp] = wmin;
+        __syncthreads();
+        int sel = s_min[par][0];
+#pragma unroll
+        for (int w = 1; w < NMS_WARPS; ++w) sel = min(sel, s_min[par][w]);
+        par ^= 1;
+        if (sel == 0x7fffffff) break;
+        float4 kb;
+        float ka;
+        const unsigned long long kkey = keys[sel];
+        if (in_smem) {
+            kb = s_box[sel];
+            ka = s_area[sel];
+        } else {
+            kb = norm_box(gboxes[key_index(kkey)], ka);
+        }
+        if (tid == 0) write_det(out, nsel, kkey, gboxes[key_index(kkey)]);
+        if (in_smem) {
+            for (unsigned m = mask0; m;) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1u;
+                const int pos = tid + q * NMS_THREADS;
+                if (pos <= sel || iou_norm_gt(kb, ka, s_box[pos], s_area[pos], p.iou)) mask0 &= ~(1u << q);
+            }
+        } else {
+            for (int w = first_w; w * 32 < slots; ++w) {
+                unsigned word = alive_g[(size_t)w * NMS_THREADS + tid];
+                for (unsigned m = word; m;) {
+                    const int q = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const int pos = tid + (w * 32 + q) * NMS_THREADS;
+                    float ar;
+                    const float4 cb = norm_box(gboxes[key_index(keys[pos])], ar);
+                    if (pos <= sel || iou_norm_gt(kb, ka, cb, ar, p.iou)) word &= ~(1u << q);
+                }
+                alive_g[(size_t)w * NMS_THREADS + tid] = word;
+            }
+        }
+        ++nsel;
     }
+    if (tid == 0) *count_out = nsel;
 }
 
 struct RegionParams {
@@ -484,16 +491,16 @@ __global__ void __launch_bounds__(DET_THREADS) region_kernel(const RegionParams 
         const int a = index / wh, loc = index - a * wh;
         const int row = loc / p.W, col = loc - row * p.W;
         const float *e = in + (size_t)a * E * wh + loc;
-        const float sx = sigmoidf_ref(__ldg(e)), sy = sigmoidf_ref(__ldg(e + wh));
+        const float sx = sigmoidf_glibc(__ldg(e)), sy = sigmoidf_glibc(__ldg(e + wh));
         const float tw = __ldg(e + 2 * wh), th = __ldg(e + 3 * wh);
-        const float conf = sigmoidf_ref(__ldg(e + 4 * wh));
+        const float conf = sigmoidf_glibc(__ldg(e + 4 * wh));
         float largest = __ldg(e + 5 * wh);
         for (int j = 1; j < p.C; ++j) largest = fmaxf(largest, __ldg(e + (5 + j) * wh));
         float sum = 0.f;
-        for (int j = 0; j < p.C; ++j) sum = __fadd_rn(sum, expf(__fsub_rn(__ldg(e + (5 + j) * wh), largest)));
+        for (int j = 0; j < p.C; ++j) sum = __fadd_rn(sum, expf_glibc(__fsub_rn(__ldg(e + (5 + j) * wh), largest)));
         float mx = 0.f;
         for (int j = 0; j < p.C; ++j) {
-            const float sm = __fdiv_rn(expf(__fsub_rn(__ldg(e + (5 + j) * wh), largest)), sum);
+            const float sm = __fdiv_rn(expf_glibc(__fsub_rn(__ldg(e + (5 + j) * wh), largest)), sum);
             const float prob = __fmul_rn(conf, sm);
             const float kept = (prob > p.thr) ? prob : 0.f;
             probs[(size_t)index * (p.C + 1) + j] = kept;
@@ -512,8 +519,8 @@ __global__ void __launch_bounds__(DET_THREADS) region_kernel(const RegionParams 
         }
         const float bx = __fdiv_rn(__fadd_rn((float)col, sx), (float)p.W);
         const float by = __fdiv_rn(__fadd_rn((float)row, sy), (float)p.H);
-        const float bw = __fmul_rn(expf(tw), p.anchors[2 * a]);
-        const float bh = __fmul_rn(expf(th), p.anchors[2 * a + 1]);
+        const float bw = __fmul_rn(expf_glibc(tw), p.anchors[2 * a]);
+        const float bh = __fmul_rn(expf_glibc(th), p.anchors[2 * a + 1]);
         float4 bb;
         bb.x = (float)__ddiv_rn(__dsub_rn((double)bx, p.dx), p.sxw);
         bb.y = (float)__ddiv_rn(__dsub_rn((double)by, p.dy), p.syh);
@@ -578,8 +585,8 @@ __global__ void __launch_bounds__(256) xywh_to_all_kernel(const float2 *__restri
     o.x = __fdiv_rn(__fadd_rn(sigmoidf_ref(t.x), (float)col), (float)W);
     o.y = __fdiv_rn(__fadd_rn(sigmoidf_ref(t.y), (float)row), (float)H);
     xy[i] = o;
-    o.x = __fmul_rn(expf(u.x), anc.wh[2 * a]);
-    o.y = __fmul_rn(expf(u.y), anc.wh[2 * a + 1]);
+    o.x = __fmul_rn(exp_cr(u.x), anc.wh[2 * a]);
+    o.y = __fmul_rn(exp_cr(u.y), anc.wh[2 * a + 1]);
     wh[i] = o;
 }
 
@@ -654,22 +661,60 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 using namespace k2y;
 
+namespace {
+constexpr int NMS_SMEM_CAP = 4096;  // candidates of one class held in shared memory (28 bytes each); more -> global-memory path
+
+struct DetectLayout {
+    size_t nbox, P, boxes_off, keys_off, ncand_off, alive_off, total;
+    int cap;
+};
+// workspace: [boxes B*nbox float4][keys B*C*P u64][ncand B*C int][alive B*C*P/32 u32]
+DetectLayout detect_layout(const k2y_detect_cfg *cfg, int batch) {
+    DetectLayout L;
+    L.nbox = 0;
+    for (int l = 0; l < cfg->n_layers; ++l) L.nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
+    L.P = (size_t)next_pow2((int)L.nbox);
+    L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 127) / 128 * 128) : (size_t)NMS_SMEM_CAP);
+    const size_t BC = (size_t)batch * cfg->class_num;
+    size_t off = 256;  // alignment slack
+    L.boxes_off = off;
+    off += align256((size_t)batch * L.nbox * sizeof(float4));
+    L.keys_off = off;
+    off += align256(BC * L.P * sizeof(unsigned long long));
+    L.ncand_off = off;
+    off += align256(BC * sizeof(int));
+    L.alive_off = off;
+    off += L.nbox > (size_t)L.cap ? align256(BC * (L.P / 32) * sizeof(unsigned)) : 0;
+    L.total = off;
+    return L;
+}
+}  // namespace
+
 extern "C" int k2y_detect_workspace_bytes(const k2y_detect_cfg *cfg, int batch, size_t *bytes) {
-    if (!cfg || !bytes || batch <= 0 || cfg->n_layers < 1 || cfg->n_layers > 3) {
+    if (!cfg || !bytes || batch <= 0 || cfg->n_layers < 1 || cfg->n_layers > 3 || cfg->anchor_num < 1 || cfg->class_num < 1) {
         set_error("k2y_detect_workspace_bytes: bad arguments");
         return K2Y_ERR_INVALID;
     }
-    size_t nbox = 0;
-    for (int l = 0; l < cfg->n_layers; ++l) nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
-    const size_t P = next_pow2((int)nbox);
-    // sort keys live in shared memory up to DET_SMEM_KEYS boxes per image; larger grids spill them to this workspace
-    *bytes = 256 + (P > (size_t)DET_SMEM_KEYS ? align256((size_t)batch * cfg->class_num * P * sizeof(unsigned long long)) : 0);
+    *bytes = detect_layout(cfg, batch).total;
     return K2Y_OK;
 }
 
 extern "C" int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *heads_dev, int batch,
                                 const float *image_hw_dev, k2y_det *dets_dev, int32_t *counts_dev, void *workspace,
                                 size_t workspace_bytes, void *stream) {
+    if (!cfg) {
+        set_error("k2y_detect_keras: cfg is NULL");
+        return K2Y_ERR_INVALID;
+    }
+    return k2y_detect_keras_strided(cfg, heads_dev, batch, image_hw_dev, dets_dev, counts_dev,
+                                    (long long)cfg->class_num * cfg->max_per_class * 6, (long long)cfg->class_num, workspace,
+                                    workspace_bytes, stream);
+}
+
+extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *const *heads_dev, int batch,
+                                        const float *image_hw_dev, k2y_det *dets_dev, int32_t *counts_dev,
+                                        long long det_image_stride_words, long long count_image_stride_words, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
     size_t need = 0;
     int rc = k2y_detect_workspace_bytes(cfg, batch, &need);
     if (rc != K2Y_OK) return rc;
@@ -677,10 +722,15 @@ extern "C" int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *h
         set_error("k2y_detect_keras: null pointer or workspace too small (%zu < %zu)", workspace_bytes, need);
         return K2Y_ERR_INVALID;
     }
-    if (cfg->anchor_num < 1 || cfg->anchor_num > 8 || cfg->class_num < 1 || cfg->max_per_class < 1) {
+    if (cfg->anchor_num > 8 || cfg->max_per_class < 1) {
         set_error("k2y_detect_keras: anchor_num must be 1..8, class_num and max_per_class >= 1");
         return K2Y_ERR_INVALID;
     }
+    if (det_image_stride_words < (long long)cfg->class_num * cfg->max_per_class * 6 || count_image_stride_words < cfg->class_num) {
+        set_error("k2y_detect_keras: image strides smaller than one image's records / counts");
+        return K2Y_ERR_INVALID;
+    }
+    const DetectLayout L = detect_layout(cfg, batch);
     KerasParams p;
     p.n_layers = cfg->n_layers;
     p.A = cfg->anchor_num;
@@ -695,55 +745,70 @@ extern "C" int k2y_detect_keras(const k2y_detect_cfg *cfg, const float *const *h
     }
     p.loff[3] = off;
     p.nbox = off;
-    p.P = next_pow2(off);
+    p.P = (int)L.P;
     for (int i = 0; i < 48; ++i) p.anchors[i] = 0.f;
     for (int i = 0; i < cfg->n_layers * cfg->anchor_num * 2; ++i) p.anchors[i] = cfg->anchors[i];
     p.in_h = (float)cfg->in_h;
     p.in_w = (float)cfg->in_w;
     p.obj = cfg->obj_thresh;
     p.iou = cfg->iou_thresh;
+    // sigmoid(t) >= obj needs t >= logit(obj); the scan skips the transcendental for logits below that with a margin of
+    // 1e-3 (+0.1 %) — about 1e4 float ulps of the sigmoid, so no candidate can be lost to it
+    p.logit_min = -__builtin_huge_valf();
+    if (cfg->obj_thresh > 0.f && cfg->obj_thresh < 1.f) {
+        const double lg = std::log((double)cfg->obj_thresh / (1.0 - (double)cfg->obj_thresh));
+        p.logit_min = (float)(lg - 1e-3 - 1e-3 * std::fabs(lg));
+    }
     p.maxk = cfg->max_per_class;
     p.image_hw = image_hw_dev;
     p.dets = dets_dev;
     p.counts = counts_dev;
-    p.keys_in_smem = p.P <= DET_SMEM_KEYS ? 1 : 0;
-    p.keys_global = (unsigned long long *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    const size_t smem = p.keys_in_smem ? (size_t)DET_WARPS * p.P * sizeof(unsigned long long) : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_keras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(DET_WARPS * DET_SMEM_KEYS * sizeof(unsigned long long))));
-        attr_set = true;
+    p.det_stride = det_image_stride_words;
+    p.cnt_stride = count_image_stride_words;
+    char *ws = reinterpret_cast<char *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255) - 256;  // layout offsets start at 256
+    p.boxes = reinterpret_cast<float4 *>(ws + L.boxes_off);
+    p.keys = reinterpret_cast<unsigned long long *>(ws + L.keys_off);
+    p.ncand = reinterpret_cast<int *>(ws + L.ncand_off);
+    p.alive = reinterpret_cast<unsigned *>(ws + L.alive_off);
+    p.cap = L.cap;
+    p.pcap = next_pow2(L.cap);
+    const size_t scan_smem = (size_t)SCAN_BOXES * (5 + p.C + 1) * sizeof(float);
+    const size_t nms_smem = (size_t)p.pcap * 8 + (size_t)p.cap * 20;  // sort keys (power-of-two extent) + boxes + areas
+    int dev = 0;
+    K2Y_CUDA_CHECK(cudaGetDevice(&dev));
+    static bool attr_set[64] = {false};  // per device: opt-in shared memory is a per-device function attribute
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set[dev] = true;
     }
-    dim3 grid((p.C + DET_WARPS - 1) / DET_WARPS, batch);
-    p.trace = nullptr;
-    const char *tr = getenv("K2Y_DET_TRACE");
-    if (tr && tr[0] == '1') {
-        K2Y_CUDA_CHECK(cudaMalloc(&p.trace, (size_t)batch * p.C * 4 * sizeof(long long)));
-        K2Y_CUDA_CHECK(cudaMemset(p.trace, 0, (size_t)batch * p.C * 4 * sizeof(long long)));
+    if (scan_smem > 96 * 1024) {
+        set_error("k2y_detect_keras: class_num %d too large for the scan kernel's shared-memory slab", p.C);
+        return K2Y_ERR_INVALID;
     }
-    launch_k(detect_keras_kernel, grid, dim3(DET_WARPS * 32), smem, (cudaStream_t)stream, p);
+    cudaStream_t st = (cudaStream_t)stream;
+    K2Y_CUDA_CHECK(cudaMemsetAsync(p.ncand, 0, (size_t)batch * p.C * sizeof(int), st));
+    dim3 sgrid((p.nbox + SCAN_BOXES - 1) / SCAN_BOXES, batch);
+    detect_scan_kernel<<<sgrid, SCAN_THREADS, scan_smem, st>>>(p);  // follows a memset: plain stream order
     K2Y_CUDA_CHECK(cudaGetLastError());
-    if (p.trace) {
-        K2Y_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
-        std::vector<long long> h((size_t)batch * p.C * 4);
-        cudaMemcpy(h.data(), p.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        cudaFree(p.trace);
-        long long mx[4] = {0, 0, 0, 0};
-        double sum[4] = {0, 0, 0, 0};
-        size_t worst = 0;
-        for (size_t i = 0; i < (size_t)batch * p.C; ++i) {
-            for (int j = 0; j < 4; ++j) {
-                sum[j] += (double)h[i * 4 + j];
-                if (h[i * 4 + j] > mx[j]) mx[j] = h[i * 4 + j];
-            }
-            if (h[i * 4] + h[i * 4 + 1] + h[i * 4 + 2] > h[worst * 4] + h[worst * 4 + 1] + h[worst * 4 + 2]) worst = i;
-        }
-        const double cnt = (double)batch * p.C;
-        fprintf(stderr, "[det-trace] cycles mean (scan %.0f sort %.0f nms %.0f n %.1f) max (scan %lld sort %lld nms %lld n %lld) worst warp: scan %lld sort %lld nms %lld n %lld\n",
-                sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, mx[0], mx[1], mx[2], mx[3], h[worst * 4], h[worst * 4 + 1],
-                h[worst * 4 + 2], h[worst * 4 + 3]);
+    launch_k(detect_nms_kernel, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
+    K2Y_CUDA_CHECK(cudaGetLastError());
+    return K2Y_OK;
+}
+
+// Parity hook: the two pinned float32 exponentials, element-wise on device arrays.
+__global__ void __launch_bounds__(256) expf_eval_kernel(const float *__restrict__ x, float *__restrict__ y, long long n, int mode) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = mode == 0 ? k2y::exp_cr(x[i]) : k2y::expf_glibc(x[i]);
+}
+extern "C" int k2y_expf_eval(int mode, const float *x_dev, float *y_dev, long long n, void *stream) {
+    if ((mode != 0 && mode != 1) || !x_dev || !y_dev || n < 0) {
+        set_error("k2y_expf_eval: mode must be 0 (correctly rounded) or 1 (glibc expf algorithm); non-null pointers");
+        return K2Y_ERR_INVALID;
     }
+    if (n == 0) return K2Y_OK;
+    expf_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, n, mode);
+    K2Y_CUDA_CHECK(cudaGetLastError());
     return K2Y_OK;
 }
 

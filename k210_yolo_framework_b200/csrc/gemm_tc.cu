@@ -995,12 +995,26 @@ float tf32_rna_host(float x) {
 // Tile width: UMMA_N is a multiple of 16 and <= 256 (two accumulator stages must fit the 512 TMEM columns).
 // Big-M layers take the whole N in one tile (A streams from HBM exactly once); small-M layers (7x10 / 14x20
 // grids) split N so that the tile count approaches the SM count.
-int g_num_sms = 0;
+int g_num_sms = 0;        // SM count / opt-in shared memory of the first device initialised (the planner's view of "a B200")
 size_t g_max_smem = 0;
-float *g_scratch = nullptr;      // split-K partials [splits][m_tiles*128][N]
-size_t g_scratch_bytes = 0;
-float *g_ones = nullptr, *g_zeros = nullptr;  // identity scale / shift for the partial pass
 constexpr int ID_LEN = 4096;
+constexpr size_t DEFAULT_SCRATCH_BYTES = (size_t)64 << 20;
+// Per-device state: function attributes (opt-in shared memory) are per device, and so are the allocations.  A net brings
+// its own split-K scratch (ConvArgs::tc_scratch), so nets on different streams never share partials; the per-device
+// default scratch below only serves the single-layer test hook (k2y_conv2d).
+struct DevState {
+    bool init = false;
+    float *scratch = nullptr;      // split-K partials [splits][m_tiles*128][N]
+    size_t scratch_bytes = 0;
+    float *ones = nullptr, *zeros = nullptr;  // identity scale / shift for the partial pass
+};
+constexpr int MAX_DEVICES = 64;
+DevState g_dev[MAX_DEVICES];
+DevState *cur_dev() {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) return nullptr;
+    return &g_dev[d];
+}
 
 // Tile width BN and split-K factor from a small cost model (SM cycles, calibrated on the device-side timelines
 // in profiles/): a work item costs  kb * max(MMA time, pipeline latency / depth) + epilogue + fixed,  the layer costs
@@ -1014,7 +1028,8 @@ int pick_cluster(int M, int nkb) {
     return ((M + BM - 1) / BM >= 2 && nkb >= 4) ? 2 : 1;
 }
 
-void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int cluster, int *bn_out, int *splits_out) {
+void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int cluster, size_t scratch_limit, int *bn_out, int *splits_out) {
+    if (scratch_limit == 0) scratch_limit = DEFAULT_SCRATCH_BYTES;
     const int n16 = (N + 15) / 16 * 16;
     const int m_tiles = (M + BM - 1) / BM;
     const int sms = g_num_sms > 0 ? g_num_sms : 148;
@@ -1058,7 +1073,7 @@ void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int 
             if (force && sp != atoi(force) && !(atoi(force) < 1 && sp == 1)) continue;
             if (sp > 1) {
                 if ((N & 3) != 0 || N > ID_LEN || nkb / sp < 12) continue;
-                if ((size_t)sp * m_tiles * BM * N * sizeof(float) > (g_scratch_bytes ? g_scratch_bytes : ((size_t)64 << 20))) continue;  // 64 MB once initialised
+                if ((size_t)sp * m_tiles * BM * N * sizeof(float) > scratch_limit) continue;
             }
             const int kb = (nkb + sp - 1) / sp;
             const long items = (long)((m_tiles + cluster - 1) / cluster) * n_tiles * sp;  // per cluster
@@ -1078,9 +1093,14 @@ void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int 
 }
 
 int tc_init() {
-    if (g_num_sms != 0) return K2Y_OK;
     int dev = 0;
     K2Y_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) {
+        set_error("tc_init: device ordinal %d out of range", dev);
+        return K2Y_ERR_INVALID;
+    }
+    DevState &ds = g_dev[dev];
+    if (ds.init) return K2Y_OK;
     cudaDeviceProp prop;
     K2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1089,15 +1109,16 @@ int tc_init() {
                                         (int)prop.sharedMemPerBlockOptin));
     K2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)prop.sharedMemPerBlockOptin));
-    g_max_smem = prop.sharedMemPerBlockOptin;
-    g_num_sms = prop.multiProcessorCount;
-    g_scratch_bytes = (size_t)64 << 20;
-    K2Y_CUDA_CHECK(cudaMalloc(&g_scratch, g_scratch_bytes));
-    K2Y_CUDA_CHECK(cudaMalloc(&g_ones, ID_LEN * sizeof(float)));
-    K2Y_CUDA_CHECK(cudaMalloc(&g_zeros, ID_LEN * sizeof(float)));
+    if (g_num_sms == 0) {
+        g_max_smem = prop.sharedMemPerBlockOptin;
+        g_num_sms = prop.multiProcessorCount;
+    }
+    K2Y_CUDA_CHECK(cudaMalloc(&ds.ones, ID_LEN * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMalloc(&ds.zeros, ID_LEN * sizeof(float)));
     std::vector<float> ones(ID_LEN, 1.f);
-    K2Y_CUDA_CHECK(cudaMemcpy(g_ones, ones.data(), ID_LEN * sizeof(float), cudaMemcpyHostToDevice));
-    K2Y_CUDA_CHECK(cudaMemset(g_zeros, 0, ID_LEN * sizeof(float)));
+    K2Y_CUDA_CHECK(cudaMemcpy(ds.ones, ones.data(), ID_LEN * sizeof(float), cudaMemcpyHostToDevice));
+    K2Y_CUDA_CHECK(cudaMemset(ds.zeros, 0, ID_LEN * sizeof(float)));
+    ds.init = true;
     return K2Y_OK;
 }
 
@@ -1187,7 +1208,9 @@ bool tc_dw_fusable(const DwArgs &dw, const ConvArgs &pw, const TcWeights &w, int
 }
 
 cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st, const DwArgs *dw) {
-    if (g_num_sms == 0) return cudaErrorNotReady;
+    DevState *ds = cur_dev();
+    if (!ds) return cudaErrorInvalidDevice;
+    if (!ds->init && tc_init() != K2Y_OK) return cudaErrorNotReady;  // first launch on this device: attributes, identity vectors
     TcParams p;
     p.dw = 0;
     p.dw_w = p.dw_scale = p.dw_shift = nullptr;
@@ -1238,7 +1261,8 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.a_boxes = p.bf16 ? 2 : 1;
     p.nkb = p.bf16 ? w.Kpad64 / 64 : w.Kpad / BK;
     p.cluster = pick_cluster(p.M, p.nkb);
-    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a) || dw, p.cluster, &p.BN, &p.k_splits);
+    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a) || dw, p.cluster, a.tc_scratch ? a.tc_scratch_bytes : 0, &p.BN,
+              &p.k_splits);
     p.n_tiles = (w.Npad + p.BN - 1) / p.BN;
     p.m_tiles = (p.M + BM - 1) / BM;
     p.kb_per_split = (p.nkb + p.k_splits - 1) / p.k_splits;
@@ -1263,17 +1287,26 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.tma_store = ((a.N & 3) == 0 && a.residual == nullptr && (((uintptr_t)a.dst) & 15) == 0) ? 1 : 0;
     if (getenv("K2Y_TC_NO_TMA_STORE") && p.k_splits == 1) p.tma_store = 0;
     const size_t mpad = (size_t)p.m_tiles * BM;
+    float *scratch = a.tc_scratch;
     if (p.k_splits > 1) {
+        if (!scratch) {  // no caller-owned scratch (k2y_conv2d): the device's default one, created on first use
+            if (!ds->scratch) {
+                cudaError_t me = cudaMalloc(&ds->scratch, DEFAULT_SCRATCH_BYTES);
+                if (me != cudaSuccess) return me;
+                ds->scratch_bytes = DEFAULT_SCRATCH_BYTES;
+            }
+            scratch = ds->scratch;
+        }
         // partial pass: raw accumulators -> scratch through the TMA-store epilogue (identity scale, no activation)
         p.tma_store = 1;
-        p.dst = g_scratch;
+        p.dst = scratch;
         p.residual = nullptr;
-        p.scale = g_ones;
-        p.shift = g_zeros;
+        p.scale = ds->ones;
+        p.shift = ds->zeros;
         p.act = ACT_NONE;
         p.act_slope = 1.f;
         p.act_clamp = __int_as_float_host(0x7f800000);
-        if (!make_map_2d(&map_out, g_scratch, (uint64_t)p.k_splits * mpad, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
+        if (!make_map_2d(&map_out, scratch, (uint64_t)p.k_splits * mpad, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
     } else if (p.tma_store && !make_map_2d(&map_out, a.dst, (uint64_t)p.M, (uint64_t)a.N, 32)) {
         return cudaErrorInvalidValue;
     }
@@ -1355,7 +1388,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         const float slope = a.act == ACT_NONE ? 1.f : (a.act == ACT_LEAKY ? a.alpha : 0.f);
         const float clamp = a.act == ACT_RELU6 ? 6.f : __int_as_float_host(0x7f800000);
         const size_t total = (size_t)p.M * (a.N / 4);
-        launch_k(splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float *)g_scratch, a.dst, a.residual,
+        launch_k(splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float *)scratch, a.dst, a.residual,
                  a.scale, a.shift, p.M, a.N, p.k_splits, mpad * a.N, slope, clamp);
         e = cudaGetLastError();
     }
@@ -1367,8 +1400,17 @@ int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode) {
     const int mode = effective_mode(a, math_mode);
     const bool bf = mode == K2Y_MATH_TC_BF16X3;
     const int M = a.B * a.OH * a.OW, nkb = bf ? w.Kpad64 / 64 : w.Kpad / BK;
-    pick_tile(M, a.N, nkb, mode != K2Y_MATH_TC_TF32, bf, !is_plain_1x1(a), pick_cluster(M, nkb), &bn, &splits);
+    pick_tile(M, a.N, nkb, mode != K2Y_MATH_TC_TF32, bf, !is_plain_1x1(a), pick_cluster(M, nkb), a.tc_scratch ? a.tc_scratch_bytes : 0, &bn, &splits);
     return splits > 1 ? 2 : 1;
+}
+
+// Upper bound of the split-K scratch a conv of this shape can ask for (8 slices of [m_tiles*128][N] partials, capped at the
+// planner's default limit); 0 when the shape is never split.  A net sizes its own scratch with the maximum over its layers.
+size_t tc_scratch_bound(const ConvArgs &a, const TcWeights &w) {
+    const int M = a.B * a.OH * a.OW;
+    if ((a.N & 3) != 0 || a.N > ID_LEN || w.Kpad / BK < 24) return 0;
+    const size_t need = (size_t)8 * ((M + BM - 1) / BM) * BM * a.N * sizeof(float);
+    return need < DEFAULT_SCRATCH_BYTES ? need : DEFAULT_SCRATCH_BYTES;
 }
 
 }  // namespace k2y
@@ -1393,7 +1435,7 @@ extern "C" int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *b
     const bool bf = mode == K2Y_MATH_TC_BF16X3, three_x = mode != K2Y_MATH_TC_TF32;
     const int nkb = bf ? (K + 63) / 64 : (K + BK - 1) / BK;
     *cluster = pick_cluster(M, nkb);
-    pick_tile(M, N, nkb, three_x, bf, gather, *cluster, bn, k_splits);
+    pick_tile(M, N, nkb, three_x, bf, gather, *cluster, 0, bn, k_splits);
     const size_t stage_bytes = (size_t)A_TILE_BYTES * (bf ? 2 : 1) + (size_t)(*bn) * 128 * (three_x ? 2 : 1);
     int st = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage_bytes);
     if (st > MAX_STAGES) st = MAX_STAGES;

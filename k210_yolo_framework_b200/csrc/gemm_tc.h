@@ -17,6 +17,7 @@ struct TcWeights {
 int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N);  // kernel_kn: [K][N] row-major (Keras HWIO flattened)
 void tc_free(TcWeights &w);
 bool tc_supported(const ConvArgs &a, const TcWeights &w);
+size_t tc_scratch_bound(const ConvArgs &a, const TcWeights &w);           // split-K scratch a net must provide for this layer
 int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode);  // kernels one launch_conv_tc issues
 // dw != nullptr: `a` is the plain 1x1 conv that follows the depthwise layer *dw; both run in one launch (tc_dw_fusable)
 cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st, const DwArgs *dw = nullptr);

@@ -12,6 +12,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.h"
@@ -85,9 +86,13 @@ struct k2y_net {
     const unsigned char *x_u8 = nullptr;  // optional uint8 input (k2y_net_bind_u8)
     int *img_max = nullptr;
     std::vector<float *> heads_dev;
-    std::map<int, cudaGraphExec_t> graphs;
+    // one captured graph per (batch, input binding): re-binding the input to an alternate buffer (double-buffered H2D) reuses
+    // the graph captured for that buffer instead of re-capturing
+    std::map<std::tuple<int, const void *, const void *, const void *>, cudaGraphExec_t> graphs;
     int last_batch = 0;
     int launches = 0;  // kernels issued by the last issue_layers() pass
+    float *tc_scratch = nullptr;   // this net's split-K partials (never shared with another net / stream)
+    size_t tc_scratch_bytes = 0;
 
     std::string auto_name(const std::string &base) {
         int n = auto_count[base]++;
@@ -308,6 +313,18 @@ void build_darknet(k2y_net *n, int out_ch) {
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Makes the net's device current for the duration of a call (function attributes, allocations and launches are per device).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 void plan_arena(k2y_net *n) {
     auto &T = n->tensors;
     for (auto &t : T) {
@@ -433,6 +450,8 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
         a.pad_l = L.pad_l;
         a.act = L.act;
         a.alpha = L.alpha;
+        a.tc_scratch = n->tc_scratch;
+        a.tc_scratch_bytes = n->tc_scratch_bytes;
         return a;
     };
     for (size_t idx = 0; idx < n->layers.size(); ++idx) {
@@ -601,6 +620,8 @@ extern "C" int k2y_net_create(const char *model_def, int in_h, int in_w, float a
 extern "C" int k2y_net_destroy(k2y_net *net) {
     if (!net) return K2Y_OK;
     drop_graphs(net);
+    cudaFree(net->tc_scratch);
+    net->tc_scratch = nullptr;
     for (Layer &L : net->layers) {
         cudaFree(L.d_w);
         cudaFree(L.d_scale);
@@ -703,7 +724,7 @@ extern "C" int k2y_net_set_weight(k2y_net *net, const char *layer, const char *v
 
 extern "C" int k2y_net_finalize(k2y_net *net) {
     if (check_net(net, "k2y_net_finalize")) return K2Y_ERR_INVALID;
-    K2Y_CUDA_CHECK(cudaSetDevice(net->device));
+    DeviceGuard guard(net->device);
     drop_graphs(net);
     for (Layer &L : net->layers) {
         if (L.kind == L_POOL) continue;
@@ -769,6 +790,28 @@ extern "C" int k2y_net_finalize(k2y_net *net) {
                 K2Y_CUDA_CHECK(cudaMemcpy(L.d_scale2, sc2.data(), 2 * N * sizeof(float), cudaMemcpyHostToDevice));
                 K2Y_CUDA_CHECK(cudaMemcpy(L.d_shift2, sh2.data(), 2 * N * sizeof(float), cudaMemcpyHostToDevice));
             }
+        }
+    }
+    // split-K scratch of this net: the largest bound over its dense convs at max_batch
+    size_t scratch = 0;
+    for (const Layer &L : net->layers) {
+        if (L.kind != L_CONV) continue;
+        const Tensor &d = net->tensors[L.dst];
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.B = net->max_batch;
+        a.OH = d.h;
+        a.OW = d.w;
+        a.N = L.cout;
+        scratch = std::max(scratch, tc_scratch_bound(a, L.tc));
+    }
+    if (scratch != net->tc_scratch_bytes) {
+        cudaFree(net->tc_scratch);
+        net->tc_scratch = nullptr;
+        net->tc_scratch_bytes = 0;
+        if (scratch) {
+            K2Y_CUDA_CHECK(cudaMalloc(&net->tc_scratch, scratch));
+            net->tc_scratch_bytes = scratch;
         }
     }
     net->finalized = true;
@@ -865,7 +908,20 @@ extern "C" int k2y_net_bind_u8(k2y_net *net, const unsigned char *x_u8_dev, int3
     }
     net->x_u8 = x_u8_dev;
     net->img_max = img_max_dev;
-    drop_graphs(net);
+    return K2Y_OK;
+}
+
+extern "C" int k2y_net_bind_input(k2y_net *net, const float *x_dev) {
+    if (check_net(net, "k2y_net_bind_input")) return K2Y_ERR_INVALID;
+    if (!net->bound) {
+        set_error("k2y_net_bind_input: call k2y_net_bind first");
+        return K2Y_ERR_STATE;
+    }
+    if (!x_dev || ((uintptr_t)x_dev & 15) != 0) {
+        set_error("k2y_net_bind_input: x_dev must be non-null and 16-byte aligned");
+        return K2Y_ERR_INVALID;
+    }
+    net->x_dev = x_dev;
     return K2Y_OK;
 }
 
@@ -880,9 +936,11 @@ extern "C" int k2y_net_run(k2y_net *net, int batch, void *stream) {
         return K2Y_ERR_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(net->device);
     net->last_batch = batch;
     if (!net->use_graph) return issue_layers(net, batch, st);
-    auto it = net->graphs.find(batch);
+    const auto key = std::make_tuple(batch, (const void *)net->x_dev, (const void *)net->x_u8, (const void *)net->img_max);
+    auto it = net->graphs.find(key);
     if (it == net->graphs.end()) {
         cudaGraph_t g = nullptr;
         cudaStream_t cap = st;
@@ -903,7 +961,7 @@ extern "C" int k2y_net_run(k2y_net *net, int batch, void *stream) {
         cudaGraphExec_t ge = nullptr;
         K2Y_CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
         cudaGraphDestroy(g);
-        it = net->graphs.emplace(batch, ge).first;
+        it = net->graphs.emplace(key, ge).first;
     }
     K2Y_CUDA_CHECK(cudaGraphLaunch(it->second, st));
     return K2Y_OK;
@@ -924,6 +982,11 @@ extern "C" int k2y_net_predict_host(k2y_net *net, const float *x_host, int batch
         return K2Y_ERR_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(net->device);
+    if (net->x_u8) {  // predict() takes float32 pixels: leave the uint8 front end, or the first conv would read the stale u8 buffer
+        net->x_u8 = nullptr;
+        net->img_max = nullptr;
+    }
     const size_t in_bytes = (size_t)batch * net->in_h * net->in_w * 3 * sizeof(float);
     K2Y_CUDA_CHECK(cudaMemcpyAsync(const_cast<float *>(net->x_dev), x_host, in_bytes, cudaMemcpyHostToDevice, st));
     int rc = k2y_net_run(net, batch, stream);
@@ -986,6 +1049,7 @@ extern "C" int k2y_net_profile(k2y_net *net, int batch, void *stream, float *ms_
         set_error("k2y_net_profile: need room for %d launches, batch 1..%d", L, net->max_batch);
         return K2Y_ERR_INVALID;
     }
+    DeviceGuard guard(net->device);
     std::vector<cudaEvent_t> ev(L + 1);
     for (auto &e : ev) K2Y_CUDA_CHECK(cudaEventCreate(&e));
     cudaStream_t st = (cudaStream_t)stream;

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <map>
+#include <memory>
 #include <mutex>
 
 #include "../../include/region_layer.h"
@@ -13,14 +14,18 @@
 
 namespace {
 
+// Device mirror of one region_layer_t.  Entries are keyed by the struct's address, remember the sizes they were allocated for
+// (a struct re-initialised with another geometry gets fresh buffers) and carry their own lock: the global mutex only
+// guards the map, so different layers run their GPU round trips concurrently.
 struct DeviceSide {
     float *in = nullptr, *out = nullptr, *probs = nullptr, *boxes = nullptr;
     void *ws = nullptr;
-    size_t ws_bytes = 0;
+    size_t ws_bytes = 0, n_out = 0, n_box = 0, n_probs = 0;
     cudaStream_t st = nullptr;
+    std::mutex mu;
 };
 std::mutex g_mu;
-std::map<region_layer_t *, DeviceSide> g_dev;
+std::map<region_layer_t *, std::shared_ptr<DeviceSide>> g_dev;
 
 void free_device(DeviceSide &d) {
     cudaFree(d.in);
@@ -29,7 +34,23 @@ void free_device(DeviceSide &d) {
     cudaFree(d.boxes);
     cudaFree(d.ws);
     if (d.st) cudaStreamDestroy(d.st);
-    d = DeviceSide();
+    d.in = d.out = d.probs = d.boxes = nullptr;
+    d.ws = nullptr;
+    d.st = nullptr;
+    d.ws_bytes = d.n_out = d.n_box = d.n_probs = 0;
+}
+
+void drop_device(region_layer_t *rl) {
+    std::shared_ptr<DeviceSide> d;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_dev.find(rl);
+        if (it == g_dev.end()) return;
+        d = it->second;
+        g_dev.erase(it);
+    }
+    std::lock_guard<std::mutex> lk(d->mu);
+    free_device(*d);
 }
 
 k2y_region_cfg make_cfg(const region_layer_t *rl) {
@@ -53,6 +74,7 @@ k2y_region_cfg make_cfg(const region_layer_t *rl) {
 
 extern "C" int region_layer_init(region_layer_t *rl, int width, int height, int channels, int origin_width,
                                  int origin_height) {
+    drop_device(rl);  // a re-initialised struct (or a reused address) must not inherit buffers sized for another layer
     rl->coords = 4;
     rl->image_width = 320;   // region_layer.c:24-25 — the firmware's display size, callers may overwrite
     rl->image_height = 224;
@@ -88,14 +110,7 @@ extern "C" int region_layer_init(region_layer_t *rl, int width, int height, int 
 }
 
 extern "C" void region_layer_deinit(region_layer_t *rl) {
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_dev.find(rl);
-        if (it != g_dev.end()) {
-            free_device(it->second);
-            g_dev.erase(it);
-        }
-    }
+    drop_device(rl);
     free(rl->output);
     free(rl->boxes);
     free(rl->probs_buf);
@@ -115,10 +130,19 @@ extern "C" void region_layer_run(region_layer_t *rl, obj_info_t *obj_info) {
         return;
     }
     k2y_region_cfg cfg = make_cfg(rl);
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceSide &d = g_dev[rl];
+    std::shared_ptr<DeviceSide> dp;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        std::shared_ptr<DeviceSide> &slot = g_dev[rl];
+        if (!slot) slot = std::make_shared<DeviceSide>();
+        dp = slot;
+    }
+    DeviceSide &d = *dp;
+    std::lock_guard<std::mutex> lk(d.mu);  // one struct is not re-entrant (as in the reference); distinct structs do not wait
+    if (d.in && (d.n_out != n_out || d.n_box != n_box || d.n_probs != n_probs)) free_device(d);
     auto fail = [&](const char *what, cudaError_t e) {
         fprintf(stderr, "region_layer_run: %s: %s\n", what, cudaGetErrorString(e));
+        free_device(d);  // never keep a half-built mirror
     };
     cudaError_t e;
     if (!d.in) {
@@ -134,6 +158,9 @@ extern "C" void region_layer_run(region_layer_t *rl, obj_info_t *obj_info) {
         if ((e = cudaMalloc(&d.boxes, n_box * 4 * sizeof(float))) != cudaSuccess) return fail("cudaMalloc", e);
         if ((e = cudaMalloc(&d.ws, ws)) != cudaSuccess) return fail("cudaMalloc", e);
         d.ws_bytes = ws;
+        d.n_out = n_out;
+        d.n_box = n_box;
+        d.n_probs = n_probs;
     }
     if ((e = cudaMemcpyAsync(d.in, rl->input, n_out * sizeof(float), cudaMemcpyHostToDevice, d.st)) != cudaSuccess)
         return fail("H2D", e);

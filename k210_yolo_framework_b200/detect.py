@@ -79,10 +79,16 @@ class KerasDetector:
             img = self._img_hw
         dets = self.dets if dets_out is None else dets_out
         counts = self.counts if counts_out is None else counts_out
+        # outputs may be strided per image (records and counts of one image adjacent inside a gather block, dist.py)
+        if (dets.dtype != torch.int32 or counts.dtype != torch.int32 or tuple(dets.shape[1:]) != (self.C, self.K, DET_WORDS) or
+                tuple(dets.stride()[1:]) != (self.K * DET_WORDS, DET_WORDS, 1) or tuple(counts.shape[1:]) != (self.C,) or
+                counts.stride(1) != 1 or dets.shape[0] < n or counts.shape[0] < n):
+            raise ValueError("dets_out must be int32 [>=N,C,K,6] dense per image, counts_out int32 [>=N,C]")
         st = stream if stream is not None else torch.cuda.current_stream(self.device_index)
         ptrs = (ctypes.c_void_p * len(heads))(*[t.data_ptr() for t in heads])
-        check(lib.k2y_detect_keras(ctypes.byref(self.cfg), ptrs, n, img.data_ptr(), dets.data_ptr(), counts.data_ptr(),
-                                   self._ws.data_ptr(), self._ws.numel(), ctypes.c_void_p(st.cuda_stream)))
+        check(lib.k2y_detect_keras_strided(ctypes.byref(self.cfg), ptrs, n, img.data_ptr(), dets.data_ptr(), counts.data_ptr(),
+                                           dets.stride(0), counts.stride(0), self._ws.data_ptr(), self._ws.numel(),
+                                           ctypes.c_void_p(st.cuda_stream)))
         return dets[:n], counts[:n]
 
     @staticmethod

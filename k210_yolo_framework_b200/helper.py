@@ -31,7 +31,22 @@ class Helper(object):
     def _read_img(self, img_path: str) -> np.ndarray:
         """tools/utils.py:339-355 (skimage.io.imread -> RGB uint8, grey -> 3 channels, alpha dropped)."""
         from PIL import Image
-        img = np.array(Image.open(img_path))
+        im = Image.open(img_path)
+        # skimage.io.imread semantics by PIL mode: palette / CMYK / YCbCr images are expanded to RGB, grey (+alpha) becomes
+        # 3 equal channels, 16/32-bit grey is scaled down to 8 bits, alpha is dropped
+        if im.mode in ("P", "CMYK", "YCbCr", "PA"):
+            im = im.convert("RGB")
+        elif im.mode in ("LA", "La"):
+            im = im.convert("L")
+        elif im.mode == "1":
+            im = im.convert("L")
+        elif im.mode in ("I", "I;16", "I;16B", "I;16L", "F"):
+            arr = np.asarray(im, dtype=np.float64)
+            hi = float(arr.max()) if arr.size else 0.0
+            im = Image.fromarray(np.clip(arr * (255.0 / hi if hi > 255.0 else 1.0), 0, 255).astype(np.uint8))
+        elif im.mode not in ("RGB", "RGBA", "L"):
+            im = im.convert("RGB")
+        img = np.asarray(im, dtype=np.uint8)
         if img.ndim != 3:
             img = np.stack([img] * 3, axis=-1)
         return img[..., :3]
@@ -61,8 +76,11 @@ class Helper(object):
         return letterbox_device(x, self.in_hw[0])
 
 
-_COLORMAP = [
-    (255, 82, 0), (0, 255, 245), (0, 61, 255), (0, 255, 112), (0, 255, 133), (255, 0, 0), (255, 163, 0),
-    (255, 102, 0), (194, 255, 0), (0, 143, 255), (51, 255, 0), (0, 82, 255), (0, 255, 41), (0, 255, 173),
-    (10, 0, 255), (173, 255, 0), (0, 255, 153), (255, 92, 0), (255, 0, 255), (255, 0, 245),
-] + [((37 * i) % 256, (91 * i + 60) % 256, (173 * i + 120) % 256) for i in range(60)]
+# Helper.colormap (tools/utils.py:89-105): 80 RGB triples, one per class id, kept as packed bytes (r,g,b,r,g,b,...)
+_COLORMAP_RGB = bytes.fromhex(
+    "ff520000fff5003dff00ff7000ff85ff0000ffa300ff6600c2ff00008fff33ff000052ff00ff2900ffad0a00ffadff00"
+    "00ff99ff5c00ff00ffff00f5800000008000808000000080800080008080808080400000c00000408000c08000400080"
+    "c00080408080c0808000400080400000c00080c0000040803de6faff06330b66ffff0747ff09e00907e6dcdcdcff095c"
+    "7009ff08ffd607ffe0ffb8060aff47ff290a07ffffe0ff086608ffff3d06ffc207ff7a0800ff14ff0829ff05990633ff"
+    "eb0cffa0961400a3ff8c8c8cfa0a0f14ff001fff00ff1f00ffe00099ff000000ffff470000ebff00adff1f00ff0bc8c8")
+_COLORMAP = [tuple(_COLORMAP_RGB[i:i + 3]) for i in range(0, len(_COLORMAP_RGB), 3)]

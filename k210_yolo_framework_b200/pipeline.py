@@ -1,10 +1,15 @@
 """Batched detection pipeline: the whole hot path behind one call.
 
 ``DetectionPipeline.detect_host(x)`` is the user-facing end-to-end call for a batch of pre-processed images
-held in (pinned) host memory: H2D copy -> network (one CUDA graph) -> fused decode+NMS -> [all-gather when the
-job spans several GPUs] -> D2H of the fixed-size record buffers.  ``step_device()`` is the same work on inputs
-already resident in HBM (what ``bench.py``'s ``value`` times).  It is the batched form of
-keras_inference.py:87-135, which the reference runs for one image per process.
+held in (pinned) host memory: H2D copy -> network (one CUDA graph) -> decode + NMS -> [all-gather when the
+job spans several GPUs] -> D2H of the fixed-size record blocks.  ``step_device()`` is the same work on inputs
+already resident in HBM (what ``bench.py``'s ``value`` times).  ``submit``/``collect`` is the streaming form.
+It is the batched form of keras_inference.py:87-135, which the reference runs for one image per process.
+
+Streams: kernels run on the caller's current stream.  With more than one rank the all-gather (and the D2H copy of
+the gathered blocks) runs on a side stream into one of two gather buffers, so the collective of batch i overlaps the
+convolutions of batch i+1; H2D copies use a third stream and land directly in one of two device input buffers the
+network is re-pointed at (one CUDA graph per buffer), so there is no staging copy.
 """
 from __future__ import annotations
 
@@ -16,6 +21,8 @@ import torch
 from . import yolonet
 from .detect import DET_WORDS, KerasDetector
 from .dist import DetectionGather
+
+SLOTS = 2
 
 
 class DetectionPipeline:
@@ -32,87 +39,111 @@ class DetectionPipeline:
         self.detector = KerasDetector(anchors, image_size, out_hw, class_num, obj_thresh, iou_thresh, max_per_class,
                                       max_batch=batch, device=self.device_index)
         dev = torch.device("cuda", self.device_index)
-        self.gather = DetectionGather(batch, class_num, max_per_class, dev, world=self.world, rank=self.rank, words=DET_WORDS)
+        self.gather = DetectionGather(batch, class_num, max_per_class, dev, world=self.world, rank=self.rank, words=DET_WORDS,
+                                      slots=SLOTS)
         self._img_hw = torch.tensor([[image_size[0], image_size[1]]] * batch, dtype=torch.float32, device=dev)
-        self._host_dets = torch.empty(self.gather.dets.shape, dtype=torch.int32).pin_memory()
-        self._host_counts = torch.empty(self.gather.counts.shape, dtype=torch.int32).pin_memory()
-        # streaming mode (submit / collect): two staging slots so that the H2D copy of batch i+1 overlaps batch i
-        self._copy_stream = torch.cuda.Stream(device=dev)
-        self._stage = [torch.empty_like(self.engine.input_buffer) for _ in range(2)]
-        self._slot_dets = [torch.empty(self.gather.dets.shape, dtype=torch.int32).pin_memory() for _ in range(2)]
-        self._slot_counts = [torch.empty(self.gather.counts.shape, dtype=torch.int32).pin_memory() for _ in range(2)]
-        self._h2d_done = [torch.cuda.Event() for _ in range(2)]
-        self._stage_free = [torch.cuda.Event() for _ in range(2)]
-        self._d2h_done = [torch.cuda.Event() for _ in range(2)]
+        self._side = torch.cuda.Stream(device=dev)          # all-gather + D2H of gathered blocks
+        self._copy_stream = torch.cuda.Stream(device=dev)   # H2D
+        self._host = [torch.empty(self.gather.bufs[0].shape, dtype=torch.int32).pin_memory() for _ in range(SLOTS)]
+        self._in_f32: Optional[List[torch.Tensor]] = None   # device input buffers of the streaming API, created on first use
+        self._in_u8: Optional[List[torch.Tensor]] = None
+        self._h2d_done = [torch.cuda.Event() for _ in range(SLOTS)]
+        self._in_free = [torch.cuda.Event() for _ in range(SLOTS)]       # network finished reading input slot
+        self._det_done = [torch.cuda.Event() for _ in range(SLOTS)]      # local block of gather slot written
+        self._gather_done = [torch.cuda.Event() for _ in range(SLOTS)]   # gather slot complete on this rank
+        self._slot_free = [torch.cuda.Event() for _ in range(SLOTS)]     # last reader of gather slot is done
+        self._d2h_done = [torch.cuda.Event() for _ in range(SLOTS)]
+        self._steps = 0
         self._submitted = 0
-        self._stage_u8 = None
 
     def set_image_shapes(self, image_hw) -> None:
         """Original (pre-letterbox) image sizes, [batch, 2] (h, w); defaults to the network input size."""
         arr = np.broadcast_to(np.asarray(image_hw, np.float32).reshape(-1, 2), (self.batch, 2))
         self._img_hw.copy_(torch.from_numpy(np.ascontiguousarray(arr)))
 
+    # -- device-resident step ---------------------------------------------------------------------------------------
+    def _step(self, n: int) -> int:
+        """Network + decode/NMS into gather slot s, then (world > 1) the all-gather on the side stream.  Returns s."""
+        s = self._steps % SLOTS
+        self._steps += 1
+        compute = torch.cuda.current_stream(self.device_index)
+        compute.wait_event(self._slot_free[s])          # whoever still reads this slot (gather / D2H two steps ago)
+        heads = self.engine.run(n)
+        dets, counts = self.gather.local(s)
+        self.detector.run(heads, self._img_hw[:n], dets_out=dets, counts_out=counts)
+        if self.world > 1:
+            self._det_done[s].record(compute)
+            self._side.wait_event(self._det_done[s])
+            self.gather.gather(s, stream=self._side)
+            self._gather_done[s].record(self._side)
+            self._slot_free[s].record(self._side)
+        return s
+
     def step_device(self, n: Optional[int] = None):
         """Network + decode/NMS (+ all-gather) on the bound device input; asynchronous.  Returns the gathered
-        (dets [world*batch, C, K, 6] int32, counts [world*batch, C]) device tensors."""
-        n = self.batch if n is None else n
-        heads = self.engine.run(n)
-        self.detector.run(heads, self._img_hw[:n], dets_out=self.gather.local_dets, counts_out=self.gather.local_counts)
-        return self.gather.gather()
+        (dets [world*batch, C, K, 6] int32, counts [world*batch, C]) device views; with world > 1 they are complete once
+        the current stream has passed ``wait_gathered()`` (the collective runs on a side stream)."""
+        s = self._step(self.batch if n is None else n)
+        self._last_slot = s
+        return self.gather.views(s)
+
+    def wait_gathered(self) -> None:
+        """Makes the current stream wait for the all-gather of the latest ``step_device``."""
+        if self.world > 1:
+            torch.cuda.current_stream(self.device_index).wait_event(self._gather_done[self._last_slot])
+
+    # -- host API ---------------------------------------------------------------------------------------------------
+    def _input_slots(self, u8: bool) -> List[torch.Tensor]:
+        if u8:
+            if self._in_u8 is None:
+                self._in_u8 = [torch.empty(self.engine.input_buffer.shape, dtype=torch.uint8, device=self.engine.input_buffer.device)
+                               for _ in range(SLOTS)]
+            return self._in_u8
+        if self._in_f32 is None:
+            self._in_f32 = [torch.empty_like(self.engine.input_buffer) for _ in range(SLOTS)]
+        return self._in_f32
 
     def detect_host(self, x_host: torch.Tensor):
         """x_host: CPU float32 (normalised) or uint8 (raw letterboxed RGB) [batch,H,W,3] tensor, pinned for an
         asynchronous copy.  Returns host tensors (dets, counts) for all images of the job, after a stream synchronise."""
-        n = x_host.shape[0]
-        if x_host.dtype == torch.uint8:
-            self.engine.enable_u8_input()[:n].copy_(x_host, non_blocking=True)
-        else:
-            self.engine.disable_u8_input()
-            self.engine.input_buffer[:n].copy_(x_host, non_blocking=True)
-        dets, counts = self.step_device(n)
-        self._host_dets.copy_(dets, non_blocking=True)
-        self._host_counts.copy_(counts, non_blocking=True)
-        torch.cuda.current_stream(self.device_index).synchronize()
-        return self._host_dets, self._host_counts
+        tk = self.submit(x_host)
+        return self.collect(tk)
 
     def submit(self, x_host: torch.Tensor) -> int:
-        """Streaming form of ``detect_host``: enqueue one batch (pinned host float32 [n,H,W,3]) and return a ticket.
-        The H2D copy runs on a side stream into a staging slot, so it overlaps the previous batch's kernels; at
-        most two batches are in flight — ``collect`` the ticket of batch i-1 before submitting batch i+1."""
+        """Streaming form of ``detect_host``: enqueue one batch (pinned host float32 or uint8 [n,H,W,3]) and return a
+        ticket.  The H2D copy runs on a side stream straight into one of two device input buffers (the network is
+        re-pointed at it), so it overlaps the previous batch's kernels; at most two batches are in flight —
+        ``collect`` the ticket of batch i-1 before submitting batch i+1."""
         n = x_host.shape[0]
-        slot = self._submitted % 2
+        slot = self._submitted % SLOTS
         self._submitted += 1
         compute = torch.cuda.current_stream(self.device_index)
-        u8 = x_host.dtype == torch.uint8
-        if u8:  # raw letterboxed RGB: 4x fewer PCIe bytes, normalisation (img / max(img)) fused into the first conv
-            if self._stage_u8 is None:
-                self._stage_u8 = [torch.empty(self.engine.input_buffer.shape, dtype=torch.uint8, device=self.engine.input_buffer.device)
-                                  for _ in range(2)]
-            stage, dst = self._stage_u8[slot], self.engine.enable_u8_input()
-        else:
-            self.engine.disable_u8_input()
-            stage, dst = self._stage[slot], self.engine.input_buffer
-        self._copy_stream.wait_event(self._stage_free[slot])
+        # raw letterboxed RGB (uint8): 4x fewer PCIe bytes, the normalisation (img / max(img)) is fused into the first conv
+        buf = self._input_slots(x_host.dtype == torch.uint8)[slot]
+        self._copy_stream.wait_event(self._in_free[slot])
         with torch.cuda.stream(self._copy_stream):
-            stage[:n].copy_(x_host, non_blocking=True)
+            buf[:n].copy_(x_host, non_blocking=True)
             self._h2d_done[slot].record(self._copy_stream)
         compute.wait_event(self._h2d_done[slot])
-        dst[:n].copy_(stage[:n], non_blocking=True)
-        self._stage_free[slot].record(compute)
-        dets, counts = self.step_device(n)
-        self._slot_dets[slot].copy_(dets, non_blocking=True)
-        self._slot_counts[slot].copy_(counts, non_blocking=True)
-        self._d2h_done[slot].record(compute)
-        return slot
+        self.engine.bind_input(buf)
+        s = self._step(n)
+        self._in_free[slot].record(compute)
+        # D2H of the gathered blocks: behind the all-gather on the side stream (world > 1), else on the compute stream
+        st = self._side if self.world > 1 else compute
+        with torch.cuda.stream(st):
+            self._host[s].copy_(self.gather.bufs[s], non_blocking=True)
+            self._d2h_done[s].record(st)
+            self._slot_free[s].record(st)
+        return s
 
     def collect(self, ticket: int):
-        """Blocks until the batch behind `ticket` is on the host; returns (dets, counts) pinned host tensors (valid
+        """Blocks until the batch behind `ticket` is on the host; returns (dets, counts) pinned host views (valid
         until the ticket's slot is reused two submits later)."""
         self._d2h_done[ticket].synchronize()
-        return self._slot_dets[ticket], self._slot_counts[ticket]
+        return DetectionGather.split(self._host[ticket], self.gather.C, self.gather.K, DET_WORDS)
 
     def launches_per_step(self) -> int:
-        return self.engine.launches_per_run() + 1  # + the fused decode/NMS kernel
+        return self.engine.launches_per_run() + 2  # + the decode scan and the per-class NMS kernel
 
     @staticmethod
     def records(dets: torch.Tensor, counts: torch.Tensor) -> List[list]:

@@ -167,15 +167,41 @@ class YoloEngine:
         if getattr(self, "_x_u8", None) is None:
             dev = torch.device("cuda", self.device_index)
             self._x_u8 = torch.empty((self.max_batch, self.in_h, self.in_w, 3), dtype=torch.uint8, device=dev)
-            self._img_max = torch.zeros((self.max_batch,), dtype=torch.int32, device=dev)
+            if getattr(self, "_img_max", None) is None:
+                self._img_max = torch.zeros((self.max_batch,), dtype=torch.int32, device=dev)
         check(lib.k2y_net_bind_u8(self._h, self._x_u8.data_ptr(), self._img_max.data_ptr()))
         self._u8_on = True
+        self._ext_input = None
         return self._x_u8
 
     def disable_u8_input(self) -> None:
         if getattr(self, "_u8_on", False):
             check(lib.k2y_net_bind_u8(self._h, None, None))
             self._u8_on = False
+
+    def bind_input(self, buf: torch.Tensor) -> None:
+        """Points the network input at `buf` (CUDA [max_batch,H,W,3], float32 or uint8) instead of the engine's own
+        buffer — the zero-copy form of double-buffered ingest (one CUDA graph is kept per input buffer)."""
+        self._bind()
+        if (not buf.is_cuda or not buf.is_contiguous() or tuple(buf.shape) != (self.max_batch, self.in_h, self.in_w, 3)
+                or buf.dtype not in (torch.float32, torch.uint8)):
+            raise ValueError(f"expected contiguous CUDA [{self.max_batch},{self.in_h},{self.in_w},3] float32 or uint8")
+        if buf.dtype == torch.uint8:
+            if getattr(self, "_img_max", None) is None:
+                self._img_max = torch.zeros((self.max_batch,), dtype=torch.int32, device=buf.device)
+            check(lib.k2y_net_bind_u8(self._h, buf.data_ptr(), self._img_max.data_ptr()))
+            self._u8_on = True
+        else:
+            self.disable_u8_input()
+            check(lib.k2y_net_bind_input(self._h, buf.data_ptr()))
+        self._ext_input = buf  # keep it alive
+
+    def unbind_input(self) -> None:
+        """Back to the engine's own float32 input buffer."""
+        if getattr(self, "_ext_input", None) is not None:
+            self.disable_u8_input()
+            check(lib.k2y_net_bind_input(self._h, self._x.data_ptr()))
+            self._ext_input = None
 
     def predict_device_u8(self, x_u8: torch.Tensor) -> List[torch.Tensor]:
         """x_u8: CUDA uint8 [N,H,W,3].  Same result as predict_device(x_u8 / max(x_u8) per image)."""
@@ -217,6 +243,7 @@ class YoloEngine:
         if n > self.max_batch:
             raise ValueError(f"batch {n} > max_batch {self.max_batch}")
         self._bind()
+        self.unbind_input()
         self.disable_u8_input()
         if x.data_ptr() != self._x.data_ptr():
             self._x[:n].copy_(x, non_blocking=True)
@@ -230,6 +257,8 @@ class YoloEngine:
         if x.ndim != 4 or x.shape[1:] != (self.in_h, self.in_w, 3):
             raise ValueError(f"expected [N,{self.in_h},{self.in_w},3], got {x.shape}")
         self._bind()
+        self.unbind_input()
+        self.disable_u8_input()  # predict() feeds float32 pixels (k2y_net_predict_host leaves the uint8 front end as well)
         outs = [np.empty((x.shape[0],) + s, np.float32) for s in self.out_shapes]
         st = torch.cuda.current_stream(self.device_index)
         for s in range(0, x.shape[0], self.max_batch):

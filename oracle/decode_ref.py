@@ -46,15 +46,25 @@ class HelperRef:
         return grid
 
 
+def exp32(x: np.ndarray) -> np.ndarray:
+    """float32 exp, DEFINED as the correctly rounded result (double-precision exp rounded once to float32).
+
+    The reference evaluates exp inside TensorFlow 1.14 (Eigen's vectorised pexp, third-party, not vendored); its last-bit
+    behaviour is not reproducible offline, and numpy's own float32 SIMD exp differs from the correctly rounded value
+    in ~40 % of the arguments.  Pinning exp to the correctly rounded value makes the score ORDER (and with it the NMS
+    survivor sets) a property of the head tensors alone; the CUDA path (csrc/detect.cu exp_cr) uses the same definition."""
+    return np.exp(np.asarray(x, f32).astype(np.float64)).astype(f32)
+
+
 def sigmoid32(x: np.ndarray) -> np.ndarray:
-    x = x.astype(f32)
-    return (f32(1) / (f32(1) + np.exp(-x, dtype=f32))).astype(f32)
+    x = np.asarray(x).astype(f32)
+    return (f32(1) / (f32(1) + exp32(-x))).astype(f32)
 
 
 def xywh_to_all(pred_xy: np.ndarray, pred_wh: np.ndarray, layer: int, h: HelperRef):
     """tools/utils.py:544-547."""
     xy = (sigmoid32(pred_xy) + h.xy_offset[layer].astype(f32)) / h.out_hw[layer][::-1].astype(f32)
-    wh = np.exp(pred_wh.astype(f32), dtype=f32) * h.anchors[layer].astype(f32)
+    wh = exp32(pred_wh) * h.anchors[layer].astype(f32)
     return xy.astype(f32), wh.astype(f32)
 
 

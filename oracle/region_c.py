@@ -111,8 +111,49 @@ class RegionLayerRef:
 # ---------------------------------------------------------------------------
 # numpy restatement
 # ---------------------------------------------------------------------------
+def _exp2f_table():
+    # T[i] = bits(2^(i/32)) - (i << 47), 2^(i/32) correctly rounded to double (glibc's __exp2f_data.tab)
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    t = np.zeros(32, np.uint64)
+    for i in range(32):
+        v = float(Decimal(2) ** (Decimal(i) / Decimal(32)))
+        t[i] = (np.float64(v).view(np.uint64) - np.uint64(i << 47)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    return t
+
+
+_EXP2F_TAB = _exp2f_table()
+
+
+def expf_glibc(x) -> np.ndarray:
+    """glibc >= 2.28 ``expf`` (sysdeps/ieee754/flt-32/e_expf.c, the algorithm the compiled reference links against),
+    restated in float64 numpy: exp(x) = 2^(k/32) * 2^(r/32), k = round(x*32/ln2), cubic in r, one rounding to float32.
+    Checked bit for bit against this host's libm in tests/test_oracle_region.py."""
+    xf = np.asarray(x, f32)
+    xd = xf.astype(np.float64)
+    shift = np.float64(6755399441055744.0)  # 0x1.8p52
+    z = np.float64(float.fromhex("0x1.71547652b82fep+5")) * xd
+    kd = z + shift
+    ki = kd.view(np.uint64) if kd.ndim else np.asarray(kd).reshape(1).view(np.uint64).reshape(())
+    kd = kd - shift
+    r = z - kd
+    with np.errstate(over="ignore"):
+        t = _EXP2F_TAB[(ki & np.uint64(31)).astype(np.int64)] + (ki << np.uint64(47))
+    s = t.view(np.float64) if isinstance(t, np.ndarray) and t.ndim else np.asarray(t, np.uint64).reshape(1).view(np.float64).reshape(())
+    c0, c1, c2 = (float.fromhex("0x1.c6af84b912394p-20"), float.fromhex("0x1.ebfce50fac4f3p-13"),
+                  float.fromhex("0x1.62e42ff0c52d6p-6"))
+    zz = c0 * r + c1
+    y = c2 * r + 1.0
+    y = zz * (r * r) + y
+    with np.errstate(over="ignore", under="ignore"):
+        out = (y * s).astype(f32)
+    out = np.where(xf > f32(88.72283172607421875), f32(np.inf), out)
+    out = np.where(xf < f32(-103.972076416015625), f32(0), out)
+    return np.where(np.isnan(xf), xf, out).astype(f32)
+
+
 def _sigmoid(x):
-    return (f32(1) / (f32(1) + np.exp(-x.astype(f32), dtype=f32))).astype(f32)
+    return (f32(1) / (f32(1) + expf_glibc(-np.asarray(x, f32)))).astype(f32)
 
 
 def _iou_center(a, b) -> f32:
@@ -146,7 +187,7 @@ def region_layer_np(chw: np.ndarray, width: int, height: int, anchors, threshold
     # forward_region_layer (:121-137)
     sx, sy, conf = _sigmoid(x[:, 0]), _sigmoid(x[:, 1]), _sigmoid(x[:, 4])
     cls = x[:, 5:]
-    e = np.exp((cls - cls.max(axis=1, keepdims=True)).astype(f32), dtype=f32)
+    e = expf_glibc((cls - cls.max(axis=1, keepdims=True)).astype(f32))
     ssum = np.zeros((A, wh), f32)
     for j in range(C):  # sequential float32 accumulation, as the C loop does
         ssum = (ssum + e[:, j]).astype(f32)
@@ -156,8 +197,8 @@ def region_layer_np(chw: np.ndarray, width: int, height: int, anchors, threshold
     row = (np.arange(wh) // width).astype(f32)
     bx = ((col[None] + sx) / f32(width)).astype(f32)
     by = ((row[None] + sy) / f32(height)).astype(f32)
-    bw = (np.exp(x[:, 2], dtype=f32) * anchors[:, 0:1]).astype(f32)
-    bh = (np.exp(x[:, 3], dtype=f32) * anchors[:, 1:2]).astype(f32)
+    bw = (expf_glibc(x[:, 2]) * anchors[:, 0:1]).astype(f32)
+    bh = (expf_glibc(x[:, 3]) * anchors[:, 1:2]).astype(f32)
     prob = (conf[:, None, :] * soft).astype(f32)  # [A, C, wh]
     probs = np.zeros((N, C + 1), f32)
     pm = np.transpose(prob, (0, 2, 1)).reshape(N, C)

@@ -76,6 +76,65 @@ def test_seeded_heads_bit_identical_sets(seed, batch, classes, out_hw, in_hw, ob
         assert max(len(i) for i in ref) > 60
 
 
+def test_more_candidates_than_shared_memory_holds(voc_anchors):
+    """One class with > 4096 candidates: the NMS kernel sorts the keys in global memory and keeps the liveness bits there."""
+    rng = np.random.default_rng(11)
+    out_hw = np.array([[40, 40], [80, 80]])
+    classes, batch = 2, 2
+    heads = []
+    for h, w in out_hw:
+        t = rng.normal(0, 1.0, (batch, h, w, 3, 5 + classes)).astype(np.float32)
+        t[..., 4:] += 2.5          # most boxes pass obj 0.5 in both classes
+        t[..., 2:4] = t[..., 2:4] * 0.3 - 2.0   # small boxes: the cap of 30 is reached only after many suppressions
+        heads.append(t.reshape(batch, h, w, -1))
+    img_hw = np.array([[640, 640], [480, 600]], np.float32)
+    det = KerasDetector(voc_anchors, [1280, 1280], out_hw, classes, 0.5, 0.4, max_per_class=30, max_batch=batch)
+    dets, counts = det.run([torch.from_numpy(t).cuda() for t in heads], img_hw)
+    got = KerasDetector.to_host(dets, counts)
+    h = decode_ref.HelperRef(voc_anchors, [1280, 1280], out_hw, classes)
+    ref = decode_ref.detect_batch_fast(heads, h, [1280, 1280], img_hw, 0.5, 0.4)
+    n_cand = [(decode_ref.decode_layers([hd[0].reshape(hd.shape[1], hd.shape[2], 3, 5 + classes) for hd in heads], h,
+                                        [1280, 1280], img_hw[0])[1] >= 0.5).sum(0).max()]
+    assert n_cand[0] > 4096
+    _compare(got, ref)
+
+
+def test_strided_outputs_match_dense(voc_anchors):
+    """k2y_detect_keras_strided: records and counts of one image adjacent inside a gather block (dist.DetectionGather)."""
+    from k210_yolo_framework_b200.dist import DetectionGather
+    rng = np.random.default_rng(5)
+    heads = [torch.from_numpy(rng.normal(0.5, 2.0, (3, h, w, 75)).astype(np.float32)).cuda() for h, w in ((7, 10), (14, 20))]
+    det = KerasDetector(voc_anchors, [224, 320], [7, 10, 14, 20], 20, 0.6, 0.5, max_batch=3)
+    d0, c0 = det.run(heads, (224, 320))
+    dense = KerasDetector.to_host(d0.clone(), c0.clone())
+    g = DetectionGather(3, 20, 30, torch.device("cuda"), world=1, rank=0)
+    dl, cl = g.local(0)
+    det.run(heads, (224, 320), dets_out=dl, counts_out=cl)
+    assert KerasDetector.to_host(*g.views(0)) == dense
+    assert sum(len(i) for i in dense) > 20
+
+
+def test_pinned_exponentials():
+    """k2y_expf_eval: mode 0 is the correctly rounded float32 exp (KERAS dialect, == oracle.decode_ref.exp32), mode 1 is
+    glibc's expf algorithm (REGION_C dialect, == this host's libm and oracle.region_c.expf_glibc) — bit for bit."""
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.normal(0, 4, 200000), rng.uniform(-104, 89, 100000), [0.0, -0.0, 88.7, 88.73, -103.9, -104.5]]).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    y = torch.empty_like(xd)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.lib.k2y_expf_eval(0, xd.data_ptr(), y.data_ptr(), x.size, st))
+    cr = y.cpu().numpy()
+    assert (cr.view(np.uint32) == decode_ref.exp32(x).view(np.uint32)).all()
+    _lib.check(_lib.lib.k2y_expf_eval(1, xd.data_ptr(), y.data_ptr(), x.size, st))
+    gl = y.cpu().numpy()
+    assert (gl.view(np.uint32) == region_c.expf_glibc(x).view(np.uint32)).all()
+    libm = ctypes.CDLL("libm.so.6")
+    libm.expf.restype = ctypes.c_float
+    libm.expf.argtypes = [ctypes.c_float]
+    sub = slice(0, 20000)
+    assert (np.array([libm.expf(float(v)) for v in x[sub]], np.float32).view(np.uint32) == gl[sub].view(np.uint32)).all()
+
+
 def test_ties_broken_by_index(voc_anchors):
     # identical logits everywhere -> equal scores; boxes of different cells do not overlap -> all kept, index ascending
     heads = [np.zeros((1, 7, 10, 75), np.float32), np.zeros((1, 14, 20, 75), np.float32)]

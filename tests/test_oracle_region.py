@@ -36,3 +36,18 @@ def test_empty_result_when_threshold_high():
     r = region_c.RegionLayerRef(10, 7, 75, 320, 224, ANCH, 0.9, 0.3)
     assert r.run(x) == []
     assert region_c.region_layer_np(x, 10, 7, ANCH, 0.9, 0.3, 320, 224)[0] == []
+
+
+def test_expf_restatement_is_libm_bit_for_bit():
+    """oracle.region_c.expf_glibc (the algorithm csrc/detect.cu restates for the REGION_C dialect) against this host's
+    libm expf — what the compiled reference region_layer.c calls — over normals, the subnormal tail and the limits."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.expf.restype = ctypes.c_float
+    libm.expf.argtypes = [ctypes.c_float]
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(0, 4, 20000), rng.uniform(-110, 95, 10000),
+                        [0.0, -0.0, 88.7228, 88.73, -103.97, -104.0, -90.0, -100.0, 1e-30, -1e-30]]).astype(np.float32)
+    want = np.array([libm.expf(float(v)) for v in x], np.float32)
+    got = region_c.expf_glibc(x)
+    assert (want.view(np.uint32) == got.view(np.uint32)).all()
