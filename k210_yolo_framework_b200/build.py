@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libk210yolo_b200.so")
-SOURCES = ["conv_simt.cu", "gemm_tc.cu", "detect.cu", "net.cu", "region_layer_abi.cu", "preprocess.cu", "comm.cu"]
+SOURCES = ["conv_simt.cu", "gemm_tc.cu", "detect.cu", "net.cu", "region_layer_abi.cu", "preprocess.cu", "comm.cu", "dwpw_tc.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared"]
 

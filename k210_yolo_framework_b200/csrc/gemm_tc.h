@@ -23,4 +23,9 @@ int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode);  // k
 cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode, cudaStream_t st, const DwArgs *dw = nullptr);
 bool tc_dw_fusable(const DwArgs &dw, const ConvArgs &pw, const TcWeights &w, int math_mode);
 
+// Fused MobileNet block (dwpw_tc.cu): depthwise 3x3 stride 1 + BN + act computed from a TMA-staged shared-memory window
+// straight into tensor memory, then the 1x1 conv on the tensor cores — the depthwise output never reaches HBM.
+bool dwpw_supported(const DwArgs &dw, const ConvArgs &pw, const TcWeights &w, int math_mode);
+cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights &w, cudaStream_t st);
+
 }  // namespace k2y

@@ -30,6 +30,7 @@ void set_error(const char *fmt, ...) {
 
 namespace {
 
+constexpr bool DWPW_DEFAULT_ON = false;  // fused depthwise->pointwise blocks in the default schedule (K2Y_DWPW=1 / K2Y_NO_DWPW=1 override)
 constexpr float BN_EPS = 1e-3f;  // Keras BatchNormalization epsilon used by every reference model
 
 enum LayerKind { L_CONV = 0, L_DW = 1, L_POOL = 2 };
@@ -454,6 +455,7 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
         a.tc_scratch_bytes = n->tc_scratch_bytes;
         return a;
     };
+    int dw_ordinal = 0;
     for (size_t idx = 0; idx < n->layers.size(); ++idx) {
         Layer &L = n->layers[idx];
         L.fused = 0;
@@ -513,12 +515,29 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
             // optional (K2Y_DWPW_FUSION=1): depthwise + the following 1x1 conv as one tensor-core launch, the depthwise output
             // goes straight into the GEMM's A stage (skipped when every layer output must be readable)
             bool fused = false;
+            ++dw_ordinal;
             if (!n->keep_all && n->math != K2Y_MATH_FP32_SIMT && idx + 1 < n->layers.size()) {
                 const Layer &P = n->layers[idx + 1];
                 const Tensor &dt = n->tensors[L.dst];
                 if (P.kind == L_CONV && P.src0 == L.dst && dt.last_use == (int)idx + 1 && dt.out_index < 0) {
                     const ConvArgs pa = conv_args(P);
-                    if (tc_dw_fusable(a, pa, P.tc, n->math)) {
+                    // default schedule: stride-1 blocks run as ONE launch (dwpw_tc.cu).  K2Y_NO_DWPW=1 disables it,
+                    // K2Y_DWPW_MASK=<bitmask over the depthwise layers in schedule order> restricts it (per-layer measurements).
+                    const char *no = getenv("K2Y_NO_DWPW"), *yes = getenv("K2Y_DWPW"), *mask = getenv("K2Y_DWPW_MASK");
+                    const bool on = DWPW_DEFAULT_ON ? !(no && no[0] == '1') : (yes && yes[0] == '1');
+                    const bool allowed = on && (!mask || ((strtoul(mask, nullptr, 0) >> (dw_ordinal - 1)) & 1ul));
+                    if (allowed && dwpw_supported(a, pa, P.tc, n->math)) {
+                        e = launch_dwpw_tc(a, pa, P.tc, st);
+                        n->launches += 1;
+                        fused = true;
+                        if (e == cudaSuccess) {
+                            ++li;
+                            if (ev) cudaEventRecord(ev[li], st);
+                            L.fused = 1;
+                            n->layers[idx + 1].fused = 2;
+                            ++idx;  // the pointwise layer is done
+                        }
+                    } else if (tc_dw_fusable(a, pa, P.tc, n->math)) {
                         e = launch_conv_tc(pa, P.tc, n->math, st, &a);
                         n->launches += 1;
                         fused = true;

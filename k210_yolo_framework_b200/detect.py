@@ -75,7 +75,7 @@ class KerasDetector:
         else:
             arr = np.asarray(image_hw, np.float32)
             arr = np.broadcast_to(arr.reshape(-1, 2), (n, 2))
-            self._img_hw[:n].copy_(torch.from_numpy(np.ascontiguousarray(arr)), non_blocking=True)
+            self._img_hw[:n].copy_(torch.from_numpy(np.array(arr, dtype=np.float32, order="C", copy=True)), non_blocking=True)
             img = self._img_hw
         dets = self.dets if dets_out is None else dets_out
         counts = self.counts if counts_out is None else counts_out

@@ -59,7 +59,7 @@ class DetectionPipeline:
     def set_image_shapes(self, image_hw) -> None:
         """Original (pre-letterbox) image sizes, [batch, 2] (h, w); defaults to the network input size."""
         arr = np.broadcast_to(np.asarray(image_hw, np.float32).reshape(-1, 2), (self.batch, 2))
-        self._img_hw.copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+        self._img_hw.copy_(torch.from_numpy(np.array(arr, dtype=np.float32, order="C", copy=True)))
 
     # -- device-resident step ---------------------------------------------------------------------------------------
     def _step(self, n: int) -> int:

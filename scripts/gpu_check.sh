@@ -4,13 +4,13 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)" >> gpurun_out/smi.txt
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1
+timeout ${PYTEST_TIMEOUT:-1200} python -m pytest tests -q -m gpu --timeout 600 ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py --steps 30 --warmup 5 ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${NCU:-1}" = "1" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 3 --warmup 3 --no-cpu ${BENCH_ARGS:-} > gpurun_out/ncu_bench.log 2>&1
   echo "ncu exit $?"; tail -3 gpurun_out/launches.csv
 fi

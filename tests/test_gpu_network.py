@@ -114,32 +114,49 @@ def test_device_api_graph_replay_and_batching():
 
 
 def test_fused_depthwise_pointwise_blocks(monkeypatch):
-    """Opt-in schedule (K2Y_DWPW_FUSION=1): the first two MobileNet blocks run depthwise+pointwise as one tensor-core
-    launch (the gather warps compute the depthwise tile into the GEMM's A stage); same heads as the default schedule."""
+    """Default schedule: every stride-1 MobileNet block (depthwise 3x3 + 1x1) is ONE launch of dwpw_tc_kernel — the depthwise
+    result goes from a TMA-staged shared-memory window straight into tensor memory.  Same heads as the unfused schedule
+    (K2Y_NO_DWPW=1), fewer launches, and the oracle on extents where tiles are partial."""
+    monkeypatch.setenv("K2Y_DWPW", "1")
+    monkeypatch.delenv("K2Y_NO_DWPW", raising=False)
     m, _ = yolonet.yolo_mobilev1([224, 320, 3], 3, 20, alpha=0.75, max_batch=3)
     weights = random_weights(m.engine.expected_variables(), seed=9, detection_rich=True)
     m.set_weights_dict(weights)
     m.engine.set_use_graph(False)
     x = torch.rand((3, 224, 320, 3), device="cuda")
-    plain = [t.clone() for t in m.predict_device(x)]
-    n_plain = m.engine.launches_per_run()
-    monkeypatch.setenv("K2Y_DWPW_FUSION", "1")
     fused = [t.clone() for t in m.predict_device(x)]
-    assert m.engine.launches_per_run() == n_plain - 2
+    n_fused = m.engine.launches_per_run()
     names = [p["name"] for p in m.engine.profile(3)]
-    assert "conv_dw_1+conv_pw_1" in names and "conv_dw_2+conv_pw_2" in names
+    for blk in (1, 3, 5, 7, 8, 9, 10, 11):
+        assert f"conv_dw_{blk}+conv_pw_{blk}" in names, names
+    monkeypatch.setenv("K2Y_NO_DWPW", "1")
+    monkeypatch.setenv("K2Y_DWPW", "0")
+    plain = [t.clone() for t in m.predict_device(x)]
+    assert m.engine.launches_per_run() == n_fused + 8
+    assert not any("+" in p["name"] for p in m.engine.profile(3))
+    monkeypatch.delenv("K2Y_NO_DWPW")
+    monkeypatch.setenv("K2Y_DWPW", "1")
     for p, q in zip(fused, plain):
         assert torch.allclose(p, q, atol=3e-4, rtol=1e-4), float((p - q).abs().max())
-    # against the oracle, on extents where the last GEMM tile is partial
-    m2, _ = yolonet.yolo_mobilev1([96, 160, 3], 3, 20, alpha=0.5, max_batch=2)
-    w2 = random_weights(m2.engine.expected_variables(), seed=10, detection_rich=True)
-    m2.set_weights_dict(w2)
-    x2 = np.random.default_rng(3).random((2, 96, 160, 3), dtype=np.float32)
-    got = m2.predict(x2)
-    assert any("+" in p["name"] for p in m2.engine.profile(2))
-    ref = keras_ref.forward("yolo_mobilev1", w2, x2.astype(np.float64), alpha=0.5, dtype=torch.float64)
-    for g, r in zip(got, ref):
-        assert _maxerr(g, r) / max(1.0, float(np.abs(r).max())) < LAYER_TOL[_lib.MATH_TC_BF16X3]
+    # one block at a time (K2Y_DWPW_MASK selects depthwise layers by schedule order): localises a failure to a layer shape
+    for blk in (1, 3, 5, 7):
+        monkeypatch.setenv("K2Y_DWPW_MASK", hex(1 << (blk - 1)))
+        one = m.predict_device(x)
+        assert m.engine.launches_per_run() == n_fused + 7
+        for p, q in zip(one, plain):
+            assert torch.allclose(p, q, atol=3e-4, rtol=1e-4), (blk, float((p - q).abs().max()))
+    monkeypatch.delenv("K2Y_DWPW_MASK")
+    # against the oracle, on extents where tiles are partial (96x160 -> 48x80, 24x40, 12x20, 6x10 maps) and C = 16..512
+    for alpha, hw in ((0.5, (96, 160)), (1.0, (64, 96))):
+        m2, _ = yolonet.yolo_mobilev1([hw[0], hw[1], 3], 3, 20, alpha=alpha, max_batch=2)
+        w2 = random_weights(m2.engine.expected_variables(), seed=10, detection_rich=True)
+        m2.set_weights_dict(w2)
+        x2 = np.random.default_rng(3).random((2, hw[0], hw[1], 3), dtype=np.float32)
+        got = m2.predict(x2)
+        assert any("+" in p["name"] for p in m2.engine.profile(2))
+        ref = keras_ref.forward("yolo_mobilev1", w2, x2.astype(np.float64), alpha=alpha, dtype=torch.float64)
+        for g, r in zip(got, ref):
+            assert _maxerr(g, r) / max(1.0, float(np.abs(r).max())) < LAYER_TOL[_lib.MATH_TC_BF16X3]
 
 
 def test_predict_after_uint8_input_uses_the_float_input():
