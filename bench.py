@@ -476,6 +476,9 @@ def run_ours(args, cfg):
             "precision_matched": ({"math": "tc_3xtf32", "value": world * B * matched["steps"] / (m_ms * 1e-3),
                                    "ms_per_step": m_ms / matched["steps"], "unit": "images/sec"} if matched else None),
             "top_launches": sorted(({"name": a["name"], "ms": round(a["ms"], 4)} for a in cands), key=lambda a: -a["ms"])[:6],
+            "launch_table": [{"name": a["name"], "us": round(a["ms"] * 1e3, 2),
+                              "floor_us": round(max(a["flops"] / (peaks["bf16_tflops"] * 1e12), a["bytes"] / (peaks["hbm_gbs"] * 1e9)) * 1e6, 2)}
+                             for a in cands if a["ms"] > 0],
         }
         out.update(parity)
         emit(json.dumps(out))

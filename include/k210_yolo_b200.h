@@ -236,6 +236,17 @@ int k2y_expf_eval(int mode, const float *x_dev, float *y_dev, long long n, void 
 int k2y_letterbox_u8(const unsigned char *src_dev, int src_h, int src_w, const double *inv_matrix_host,
                      unsigned char *dst_dev, int dst_h, int dst_w, int *minmax_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Evaluation: the counters behind the reference's Yolo_Precision / Yolo_Recall metrics (tools/custom.py:13-75) on device
+ * tensors.  y_true_dev / y_pred_dev: n_boxes records of entry_floats = 5 + classes floats (any [..., A, 5+C] head or label
+ * tensor, flattened); element 4 is the confidence.  counts_dev[3] (uint64, caller-zeroed, accumulated into): tp, fp, fn with
+ *   tp: true > thr && pred > thr;  fp: !(true > thr) && pred > thr;  fn: true > thr && !(pred > thr)
+ * precision = tp / (tp + fp), recall = tp / (tp + fn) (0 when the denominator is 0).  apply_sigmoid = 0 reproduces the
+ * reference (raw logit against the threshold), 1 compares sigmoid(pred).
+ * ---------------------------------------------------------------------------------------- */
+int k2y_pr_counts(const float *y_true_dev, const float *y_pred_dev, long long n_boxes, int entry_floats, float threshold,
+                  int apply_sigmoid, unsigned long long *counts_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

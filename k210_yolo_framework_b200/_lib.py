@@ -99,6 +99,7 @@ _SIGNATURES = {
     "k2y_nms_workspace_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "k2y_nms_boxes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "k2y_expf_eval": (c_int, [c_int, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    "k2y_pr_counts": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_int, c_void_p, c_void_p]),
     "k2y_letterbox_u8": (c_int, [c_void_p, c_int, c_int, POINTER(ctypes.c_double), c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 # include/region_layer.h (ABI-compatible firmware API)

@@ -7,9 +7,9 @@
 //                       sigmoid(conf) is evaluated once per box, every box is decoded once (tf_xywh_to_all + correct_box)
 //                       into a per-image box table, and every (box, class) with score >= obj_thresh appends its sort key
 //                       (score bits << 32 | ~index) to the class's candidate list.
-//   detect_nms_kernel   CTA = one (image, class): CTA-wide bitonic sort of the keys in shared memory, candidate boxes
-//                       gathered from the box table, then the greedy selection as <= max_per_class rounds of
-//                       "first candidate still alive -> keep -> every thread tests its candidates against it".
+//   detect_nms_kernel   CTA = one (image, class): candidate keys and boxes (gathered from the box table) in shared memory,
+//                       then the greedy selection as <= max_per_class rounds of "best candidate still alive (CTA-wide
+//                       arg-max, no sort) -> keep -> every thread tests its candidates against it".
 // REGION_C: one CTA per image (softmax + decode by all threads, then one warp per class).
 //
 // Arithmetic is float32 in the reference's operation order with explicit round-to-nearest intrinsics where FMA
@@ -173,7 +173,7 @@ struct KerasParams {
     unsigned long long *keys;         // [B][C][P] candidate sort keys
     int *ncand;                       // [B][C] candidates per (image, class); zeroed before the scan
     unsigned *alive;                  // [B][C][P/32] (only used when a class has more candidates than fit shared memory)
-    int cap, pcap;                    // candidates the NMS kernel can hold in shared memory; pcap = next power of two (sort extent)
+    int cap;                          // candidates the NMS kernel can hold in shared memory (keys 8 B + box 16 B + area 4 B each)
 };
 
 // Collects the candidates of one class (score passes `pred`) in index order, sorts them.
@@ -295,28 +295,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
     }
 }
 
-// ---- pass 2: sort + greedy NMS.  grid = (C, B), one CTA per (image, class) --------------------------------------------
-constexpr int NMS_THREADS = 128;
+// ---- pass 2: greedy NMS by repeated selection.  grid = (C, B), one CTA per (image, class) ------------------------------
+// tf.image.non_max_suppression visits candidates in descending score and keeps one iff no box kept earlier overlaps it by
+// more than the threshold.  Equivalently: repeat { take the best candidate still alive, keep it, kill everything it
+// overlaps } — at most max_per_class rounds, with NO sort: a round is an arg-max over the live candidates (three
+// warp-reduce instructions on the (score bits, ~index, position) triple + one shared-memory exchange) followed by one
+// IoU test per live candidate, all candidates spread over the CTA's threads.  The selection order is exactly the order of
+// the sorted keys (score descending, index ascending), so the records equal the sequential algorithm's.
+constexpr int NMS_THREADS = 256;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
-
-// CTA-wide bitonic sort (descending) of P (power of two >= 64) keys in shared or global memory.
-__device__ __forceinline__ void cta_sort_desc(unsigned long long *keys, int P, int tid) {
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += NMS_THREADS) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // t with a 0 inserted at bit log2(j)
-                const int ixj = i | j;
-                const unsigned long long a = keys[i], b = keys[ixj];
-                const bool desc = ((i & k) == 0);
-                if (desc ? (a < b) : (a > b)) {
-                    keys[i] = b;
-                    keys[ixj] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
 
 __device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long long key, const float4 kb) {
     k2y_det d;
@@ -329,9 +316,107 @@ __device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long 
     out[slot] = d;
 }
 
+template <bool SMEM>
+__device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const unsigned long long *keys, const float4 *s_box, const float *s_area,
+                                          const float4 *gboxes, unsigned *alive_g, k2y_det *out, int (*s_red)[NMS_WARPS][3]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // candidate `pos` belongs to thread pos % NMS_THREADS; its liveness is bit (pos / NMS_THREADS) % 32 of the thread's mask word
+    // (pos / NMS_THREADS) / 32 — one register in the shared-memory path (cap <= 32 * NMS_THREADS), global words otherwise
+    const int slots = n > tid ? (n - tid + NMS_THREADS - 1) / NMS_THREADS : 0;
+    const int nwords = (slots + 31) >> 5;
+    unsigned mask0 = 0u;
+    if (SMEM) {
+        mask0 = slots >= 32 ? 0xffffffffu : ((1u << slots) - 1u);
+    } else {
+        for (int w = 0; w < nwords; ++w) {
+            const int left = slots - w * 32;
+            alive_g[(size_t)w * NMS_THREADS + tid] = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        }
+    }
+    int nsel = 0, par = 0;
+    while (nsel < p.maxk) {
+        // ---- best live candidate of this thread ----
+        unsigned long long best = 0ull;
+        int bpos = -1;
+        for (int w = 0; w < (SMEM ? 1 : nwords); ++w) {
+            for (unsigned m = SMEM ? mask0 : alive_g[(size_t)w * NMS_THREADS + tid]; m;) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1u;
+                const int pos = tid + (w * 32 + q) * NMS_THREADS;
+                const unsigned long long k = keys[pos];
+                if (bpos < 0 || k > best) {
+                    best = k;
+                    bpos = pos;
+                }
+            }
+        }
+        // ---- arg-max over the CTA: (score bits, ~index) lexicographic; keys are unique, so the winner is ----
+        const unsigned hi = bpos >= 0 ? (unsigned)(best >> 32) : 0u;
+        const unsigned mhi = __reduce_max_sync(FULL, hi);
+        const unsigned lo = (bpos >= 0 && hi == mhi) ? (unsigned)best : 0u;
+        const unsigned mlo = __reduce_max_sync(FULL, lo);
+        const int cpos = (bpos >= 0 && hi == mhi && lo == mlo) ? bpos : 0x7fffffff;
+        const int mpos = __reduce_min_sync(FULL, cpos);
+        if (lane == 0) {
+            s_red[par][warp][0] = (int)mhi;
+            s_red[par][warp][1] = (int)mlo;
+            s_red[par][warp][2] = mpos;
+        }
+        __syncthreads();
+        unsigned whi = 0u, wlo = 0u;
+        int wpos = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < NMS_WARPS; ++w) {
+            const unsigned h2 = (unsigned)s_red[par][w][0], l2 = (unsigned)s_red[par][w][1];
+            const int p2 = s_red[par][w][2];
+            if (p2 != 0x7fffffff && (wpos == 0x7fffffff || h2 > whi || (h2 == whi && l2 > wlo))) {
+                whi = h2;
+                wlo = l2;
+                wpos = p2;
+            }
+        }
+        par ^= 1;
+        if (wpos == 0x7fffffff) break;   // nothing alive
+        const unsigned long long wkey = ((unsigned long long)whi << 32) | wlo;
+        float4 kb;
+        float ka;
+        if (SMEM) {
+            kb = s_box[wpos];
+            ka = s_area[wpos];
+        } else {
+            kb = norm_box(gboxes[key_index(wkey)], ka);
+        }
+        if (tid == 0) write_det(out, nsel, wkey, gboxes[key_index(wkey)]);
+        // ---- the kept box kills what it overlaps (and itself) ----
+        for (int w = 0; w < (SMEM ? 1 : nwords); ++w) {
+            unsigned word = SMEM ? mask0 : alive_g[(size_t)w * NMS_THREADS + tid];
+            for (unsigned m = word; m;) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1u;
+                const int pos = tid + (w * 32 + q) * NMS_THREADS;
+                bool kill = pos == wpos;
+                if (!kill) {
+                    if (SMEM) {
+                        kill = iou_norm_gt(kb, ka, s_box[pos], s_area[pos], p.iou);
+                    } else {
+                        float ar;
+                        const float4 cb = norm_box(gboxes[key_index(keys[pos])], ar);
+                        kill = iou_norm_gt(kb, ka, cb, ar, p.iou);
+                    }
+                }
+                if (kill) word &= ~(1u << q);
+            }
+            if (SMEM) mask0 = word;
+            else alive_g[(size_t)w * NMS_THREADS + tid] = word;
+        }
+        ++nsel;
+    }
+    return nsel;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasParams p) {
     extern __shared__ __align__(16) unsigned char s_nms[];
-    __shared__ int s_min[2][NMS_WARPS];
+    __shared__ int s_red[2][NMS_WARPS][3];
     pdl_trigger();
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
@@ -342,7 +427,7 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
         if (tid == 0) *count_out = 0;
         return;
     }
-    unsigned long long *gkeys = p.keys + ((size_t)b * p.C + c) * p.P;
+    const unsigned long long *gkeys = p.keys + ((size_t)b * p.C + c) * p.P;
     const float4 *gboxes = p.boxes + (size_t)b * p.nbox;
 
     if (n <= 32) {
@@ -376,88 +461,24 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
         return;
     }
 
-    int P2 = 64;
-    while (P2 < n) P2 <<= 1;
-    const bool in_smem = n <= p.cap;
-    unsigned long long *keys = in_smem ? reinterpret_cast<unsigned long long *>(s_nms) : gkeys;
-    float4 *s_box = reinterpret_cast<float4 *>(s_nms + (size_t)p.pcap * 8);   // (min,max)-normalised candidate boxes
-    float *s_area = reinterpret_cast<float *>(s_nms + (size_t)p.pcap * 8 + (size_t)p.cap * 16);
-    if (in_smem) {
-        for (int i = tid; i < P2; i += NMS_THREADS) keys[i] = i < n ? gkeys[i] : 0ull;
-    } else {
-        for (int i = n + tid; i < P2; i += NMS_THREADS) keys[i] = 0ull;
-    }
-    __syncthreads();
-    cta_sort_desc(keys, P2, tid);
-    // candidate `pos` (sorted order) belongs to thread pos % 128; its liveness is bit (pos / 128) % 32 of mask word (pos / 128) / 32
-    unsigned *alive_g = p.alive + ((size_t)b * p.C + c) * (size_t)(p.P >> 5);
-    const int slots = (n - tid + NMS_THREADS - 1) / NMS_THREADS;  // candidates this thread owns (n > 32 >= ... may be 0 for high tids)
-    unsigned mask0 = 0u;                                            // smem path: <= 32 slots per thread (cap <= 4096)
-    if (in_smem) {
-        for (int q = 0; q < slots; ++q) {
-            const int pos = tid + q * NMS_THREADS;
+    int nsel;
+    if (n <= p.cap) {
+        // keys, (min,max)-normalised boxes and areas of all candidates in shared memory (arrival order: no sort needed)
+        unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_nms);
+        float4 *s_box = reinterpret_cast<float4 *>(s_nms + (size_t)p.cap * 8);
+        float *s_area = reinterpret_cast<float *>(s_nms + (size_t)p.cap * 24);
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const unsigned long long k = gkeys[i];
+            s_keys[i] = k;
             float ar;
-            s_box[pos] = norm_box(gboxes[key_index(keys[pos])], ar);
-            s_area[pos] = ar;
+            s_box[i] = norm_box(gboxes[key_index(k)], ar);
+            s_area[i] = ar;
         }
-        mask0 = slots >= 32 ? 0xffffffffu : ((1u << slots) - 1u);
-    } else {
-        for (int w = 0; w * 32 < slots; ++w) {
-            const int left = slots - w * 32;
-            alive_g[(size_t)w * NMS_THREADS + tid] = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-        }
-    }
-    __syncthreads();
-    int nsel = 0, par = 0;
-    int first_w = 0;  // global path: first mask word of this thread that may still be non-zero
-    while (nsel < p.maxk) {
-        int my = 0x7fffffff;
-        if (in_smem) {
-            if (mask0) my = tid + (__ffs(mask0) - 1) * NMS_THREADS;
-        } else {
-            while (first_w * 32 < slots && alive_g[(size_t)first_w * NMS_THREADS + tid] == 0u) ++first_w;
-            if (first_w * 32 < slots) my = tid + (first_w * 32 + __ffs(alive_g[(size_t)first_w * NMS_THREADS + tid]) - 1) * NMS_THREADS;
-        }
-        const int wmin = __reduce_min_sync(FULL, my);
-        if (lane == 0) s_min[par][warp] = wmin;
         __syncthreads();
-        int sel = s_min[par][0];
-#pragma unroll
-        for (int w = 1; w < NMS_WARPS; ++w) sel = min(sel, s_min[par][w]);
-        par ^= 1;
-        if (sel == 0x7fffffff) break;
-        float4 kb;
-        float ka;
-        const unsigned long long kkey = keys[sel];
-        if (in_smem) {
-            kb = s_box[sel];
-            ka = s_area[sel];
-        } else {
-            kb = norm_box(gboxes[key_index(kkey)], ka);
-        }
-        if (tid == 0) write_det(out, nsel, kkey, gboxes[key_index(kkey)]);
-        if (in_smem) {
-            for (unsigned m = mask0; m;) {
-                const int q = __ffs(m) - 1;
-                m &= m - 1u;
-                const int pos = tid + q * NMS_THREADS;
-                if (pos <= sel || iou_norm_gt(kb, ka, s_box[pos], s_area[pos], p.iou)) mask0 &= ~(1u << q);
-            }
-        } else {
-            for (int w = first_w; w * 32 < slots; ++w) {
-                unsigned word = alive_g[(size_t)w * NMS_THREADS + tid];
-                for (unsigned m = word; m;) {
-                    const int q = __ffs(m) - 1;
-                    m &= m - 1u;
-                    const int pos = tid + (w * 32 + q) * NMS_THREADS;
-                    float ar;
-                    const float4 cb = norm_box(gboxes[key_index(keys[pos])], ar);
-                    if (pos <= sel || iou_norm_gt(kb, ka, cb, ar, p.iou)) word &= ~(1u << q);
-                }
-                alive_g[(size_t)w * NMS_THREADS + tid] = word;
-            }
-        }
-        ++nsel;
+        nsel = nms_rounds<true>(p, n, s_keys, s_box, s_area, gboxes, nullptr, out, s_red);
+    } else {
+        unsigned *alive_g = p.alive + ((size_t)b * p.C + c) * (size_t)(p.P >> 5);
+        nsel = nms_rounds<false>(p, n, gkeys, nullptr, nullptr, gboxes, alive_g, out, s_red);
     }
     if (tid == 0) *count_out = nsel;
 }
@@ -674,7 +695,7 @@ DetectLayout detect_layout(const k2y_detect_cfg *cfg, int batch) {
     L.nbox = 0;
     for (int l = 0; l < cfg->n_layers; ++l) L.nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
     L.P = (size_t)next_pow2((int)L.nbox);
-    L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 127) / 128 * 128) : (size_t)NMS_SMEM_CAP);
+    L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 255) / 256 * 256) : (size_t)NMS_SMEM_CAP);
     const size_t BC = (size_t)batch * cfg->class_num;
     size_t off = 256;  // alignment slack
     L.boxes_off = off;
@@ -771,9 +792,8 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     p.ncand = reinterpret_cast<int *>(ws + L.ncand_off);
     p.alive = reinterpret_cast<unsigned *>(ws + L.alive_off);
     p.cap = L.cap;
-    p.pcap = next_pow2(L.cap);
     const size_t scan_smem = (size_t)SCAN_BOXES * (5 + p.C + 1) * sizeof(float);
-    const size_t nms_smem = (size_t)p.pcap * 8 + (size_t)p.cap * 20;  // sort keys (power-of-two extent) + boxes + areas
+    const size_t nms_smem = (size_t)p.cap * 28;  // keys + boxes + areas
     int dev = 0;
     K2Y_CUDA_CHECK(cudaGetDevice(&dev));
     static bool attr_set[64] = {false};  // per device: opt-in shared memory is a per-device function attribute

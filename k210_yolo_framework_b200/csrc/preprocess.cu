@@ -102,3 +102,52 @@ extern "C" int k2y_letterbox_u8(const unsigned char *src_dev, int src_h, int src
     K2Y_CUDA_CHECK(cudaGetLastError());
     return K2Y_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Precision / recall counters of the reference's training-time metrics (tools/custom.py:13-75 Yolo_Precision / Yolo_Recall),
+// evaluated on device head tensors: per box, true_conf = y_true[..., 4], pred_conf = y_pred[..., 4];
+//   tp += (true > thr) & (pred > thr);  fp += !(true > thr) & (pred > thr);  fn += (true > thr) & !(pred > thr).
+// The reference compares the RAW predicted logit with the threshold (it computes the sigmoid and never uses it, :33-35);
+// apply_sigmoid = 1 evaluates the evidently intended sigmoid(pred) > thr instead.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) pr_counts_kernel(const float *__restrict__ y_true, const float *__restrict__ y_pred, long long n_boxes,
+                                                        int entry, float thr, int apply_sigmoid, unsigned long long *__restrict__ counts) {
+    unsigned tp = 0, fp = 0, fn = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_boxes; i += (long long)gridDim.x * blockDim.x) {
+        const float t = __ldg(y_true + i * entry + 4);
+        float p = __ldg(y_pred + i * entry + 4);
+        if (apply_sigmoid) p = __fdiv_rn(1.0f, __fadd_rn(1.0f, __double2float_rn(exp(-(double)p))));
+        const bool tt = t > thr, pp = p > thr;
+        tp += tt && pp;
+        fp += !tt && pp;
+        fn += tt && !pp;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tp += __shfl_xor_sync(0xffffffffu, tp, o);
+        fp += __shfl_xor_sync(0xffffffffu, fp, o);
+        fn += __shfl_xor_sync(0xffffffffu, fn, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (tp) atomicAdd(counts + 0, (unsigned long long)tp);
+        if (fp) atomicAdd(counts + 1, (unsigned long long)fp);
+        if (fn) atomicAdd(counts + 2, (unsigned long long)fn);
+    }
+}
+}  // namespace
+
+extern "C" int k2y_pr_counts(const float *y_true_dev, const float *y_pred_dev, long long n_boxes, int entry_floats, float threshold,
+                             int apply_sigmoid, unsigned long long *counts_dev, void *stream) {
+    if (!y_true_dev || !y_pred_dev || !counts_dev || n_boxes < 0 || entry_floats < 5) {
+        k2y::set_error("k2y_pr_counts: bad arguments (entry_floats = 5 + classes >= 5)");
+        return K2Y_ERR_INVALID;
+    }
+    if (n_boxes == 0) return K2Y_OK;
+    long long blocks = (n_boxes + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pr_counts_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y_true_dev, y_pred_dev, n_boxes, entry_floats, threshold,
+                                                                       apply_sigmoid, counts_dev);
+    K2Y_CUDA_CHECK(cudaGetLastError());
+    return K2Y_OK;
+}

@@ -95,6 +95,10 @@ class YoloEngine:
                 exp[bn] = {v: (L.cout,) for v in ("gamma", "beta", "moving_mean", "moving_variance")}
         return exp
 
+    def bn_pairs(self) -> Dict[str, str]:
+        """{conv layer: the BatchNormalization layer folded behind it ('' if none)}, in creation order."""
+        return {L.name.decode(): L.bn_name.decode() for L in self.layers()}
+
     # -- weights -------------------------------------------------------------
     def set_weights(self, weights: Weights) -> None:
         _lib.require_cuda()

@@ -67,30 +67,9 @@ def main(ckpt_weights, image_size, output_size, model_def, class_num, depth_mult
 
 
 def _draw(orig_img, image_shape, found, h, out_path):
-    """keras_inference.py:137-174 — rectangles + '{class} {score:.2f}' labels; saved instead of shown."""
-    from PIL import Image, ImageDraw, ImageFont
-    pil_img = Image.fromarray(orig_img)
-    try:
-        font = ImageFont.truetype(font='asset/FiraMono-Medium.otf', size=int(np.floor(3e-2 * image_shape[0] + 0.5)))
-    except OSError:
-        font = ImageFont.load_default()
-    thickness = (image_shape[0] + image_shape[1]) // 300
-    for c, _idx, score, top, left, bottom, right in found:
-        label = '{:2d} {:.2f}'.format(int(c), score)
-        draw = ImageDraw.Draw(pil_img)
-        box = draw.textbbox((0, 0), label, font=font)
-        label_size = np.array([box[2] - box[0], box[3] - box[1]])
-        top = max(0, int(np.floor(top + 0.5)))
-        left = max(0, int(np.floor(left + 0.5)))
-        bottom = min(image_shape[0], int(np.floor(bottom + 0.5)))
-        right = min(image_shape[1], int(np.floor(right + 0.5)))
-        text_origin = np.array([left, top - label_size[1]]) if top - image_shape[0] >= 0 else np.array([left, top + 1])
-        for j in range(max(thickness, 1)):
-            draw.rectangle([left + j, top + j, right - j, bottom - j], outline=h.colormap[c])
-        draw.rectangle([tuple(text_origin), tuple(text_origin + label_size)], fill=h.colormap[c])
-        draw.text(tuple(text_origin), label, fill=(0, 0, 0), font=font)
-        del draw
-    pil_img.save(out_path)
+    """keras_inference.py:137-174 — rectangles + '{class} {score:.2f}' labels (k210_yolo_framework_b200/draw.py); saved, not shown."""
+    from k210_yolo_framework_b200.draw import draw_detections
+    draw_detections(orig_img, found, h.colormap).save(out_path)
 
 
 if __name__ == "__main__":
