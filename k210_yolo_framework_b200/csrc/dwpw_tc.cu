@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -35,7 +36,7 @@ namespace {
 
 using namespace ptx;
 
-constexpr int DP_THREADS = 14 * 32;
+constexpr int DP_THREADS = 18 * 32;   // warp 0 TMA, warp 1 MMA, warps 2-9 depthwise, warps 10-17 epilogue
 constexpr int WIN_STAGES = 3;
 constexpr int B_STAGES = 2;
 constexpr int MAX_A_STAGES = 4;
@@ -49,23 +50,35 @@ struct DwPwParams {
     int win_cols, win_rows;
     uint32_t win_bytes;         // bytes one window chunk occupies in shared memory (1024-aligned)
     uint32_t win_tx;            // bytes the TMA actually delivers per chunk
-    int acc_stages, a_stages;
+    int acc_stages, a_stages, stg_bufs;
     uint32_t tmem_cols;
-    const float *dw_w, *dw_scale, *dw_shift;   // [9][C], [C], [C]
+    const float *dw_pack;       // [11][cpad]: 9 tap rows, folded-BN scale, shift (zero beyond C)
     int dw_act;
     float dw_alpha;
-    const float *scale, *shift;                // pointwise folded BN [N]
+    const float *scale, *shift; // pointwise folded BN [N]
     int act;
     float act_slope;
     // shared-memory carve (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ss, off_dw, off_bars, cpad;
+    long long *trace;           // optional [grid][64] globaltimer stamps (K2Y_TC_TRACE=1)
 };
+
+__device__ __forceinline__ long long gtime_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DP_TRACE(slot)                                                            \
+    do {                                                                          \
+        if (p.trace) p.trace[(size_t)blockIdx.x * 64 + (slot)] = gtime_ns();      \
+    } while (0)
 
 struct __align__(8) DpBarriers {
     uint64_t win_full[WIN_STAGES], win_empty[WIN_STAGES];
     uint64_t b_full[B_STAGES], b_empty[B_STAGES];
     uint64_t a_full[MAX_A_STAGES], a_empty[MAX_A_STAGES];
     uint64_t tmem_full[2], tmem_empty[2];
+    uint64_t par_full;
     uint32_t tmem_slot;
 };
 
@@ -80,12 +93,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t sr
                  "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
-// 16 lanes x 16 columns of tensor memory: lane t of the warp writes rows t/4 (r0,r1 | r4,r5) and t/4 + 8 (r2,r3 | r6,r7), columns
-// 2*(t%4) + {0,1} (r0..r3) and 8 + 2*(t%4) + {0,1} (r4..r7), relative to the address
-__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
                  : "memory");
+}
+// 16 lanes x 8 columns of tensor memory: lane t of the warp writes row t/4 (r0, r1) and row t/4 + 8 (r2, r3), columns
+// 2*(t%4) + {0,1}, relative to the address
+__device__ __forceinline__ void tmem_st_16x256b_x1(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 __device__ __forceinline__ float dw_act_f(float v, int act, float alpha) {
     if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -101,16 +117,17 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     DpBarriers *bars = reinterpret_cast<DpBarriers *>(smem_gen + p.off_bars);
-    float *s_dw = reinterpret_cast<float *>(smem_gen + p.off_dw);   // [9][cpad] taps, [cpad] scale, [cpad] shift
-    const uint32_t b_plane = (uint32_t)p.BN * 128u;                 // one bf16 weight plane of a k-block: BN rows x 128 B
+    const float *s_dw = reinterpret_cast<const float *>(smem_gen + p.off_dw);   // [9][cpad] taps, [cpad] scale, [cpad] shift
+    const uint32_t b_plane = (uint32_t)p.BN * 128u;                              // one bf16 weight plane of a k-block: BN rows x 128 B
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
 
     if (threadIdx.x == 0) {
+        DP_TRACE(0);
         for (int s = 0; s < WIN_STAGES; ++s) {
             mbar_init(smem_u32(&bars->win_full[s]), 1);
-            mbar_init(smem_u32(&bars->win_empty[s]), 128);
+            mbar_init(smem_u32(&bars->win_empty[s]), 256);
         }
         for (int s = 0; s < B_STAGES; ++s) {
             mbar_init(smem_u32(&bars->b_full[s]), 1);
@@ -122,22 +139,21 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&bars->tmem_full[a]), 1);
-            mbar_init(smem_u32(&bars->tmem_empty[a]), 128);
+            mbar_init(smem_u32(&bars->tmem_empty[a]), 256);
         }
+        mbar_init(smem_u32(&bars->par_full), 1);
         fence_barrier_init();
+        // the depthwise taps + folded BN of this layer: constants, not produced by a predecessor -> one bulk copy, before the
+        // dependency wait
+        const uint32_t par_bytes = 11u * p.cpad * 4u;
+        mbar_arrive_expect_tx(smem_u32(&bars->par_full), par_bytes);
+        bulk_copy_g2s(smem_base + p.off_dw, p.dw_pack, par_bytes, smem_u32(&bars->par_full));
         prefetch_tmap(&map_in);
         prefetch_tmap(&map_bhi);
         prefetch_tmap(&map_blo);
         prefetch_tmap(&map_out);
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_slot), p.tmem_cols);
-    // constants of the launch (weights of this layer, not produced by a predecessor): staged before the dependency wait
-    for (int i = threadIdx.x; i < 11 * (int)p.cpad; i += DP_THREADS) {
-        const int row = i / (int)p.cpad, c = i - row * (int)p.cpad;
-        float v = 0.f;
-        if (c < p.C) v = row < 9 ? __ldg(p.dw_w + row * p.C + c) : (row == 9 ? __ldg(p.dw_scale + c) : __ldg(p.dw_shift + c));
-        s_dw[i] = v;
-    }
     {
         float *ss = reinterpret_cast<float *>(smem_gen + p.off_ss);   // [n_pass*BN] scale, then shift
         const int ncol = p.n_pass * p.BN;
@@ -151,6 +167,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_slot;
     pdl_wait();  // everything above overlaps the previous kernel's tail; the activations below do not
+    if (threadIdx.x == 0) DP_TRACE(1);
 
     const int acc_cols = p.n_pass * p.BN;
     const uint32_t tmem_a0 = tmem_base + (uint32_t)(p.acc_stages * acc_cols);   // A stages: 64 columns each (hi 32 | mid 32)
@@ -175,6 +192,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                         const uint32_t fb = smem_u32(&bars->win_full[s]);
                         mbar_arrive_expect_tx(fb, p.win_tx);
                         tma_load_4d(win_slot((int)s), &map_in, fb, c0, x0 - 1, y0 - 1, b);
+                        if (t == (int)blockIdx.x && wseq < 6) DP_TRACE(2 + wseq);
                     }
                     __syncwarp();
                     ++wseq;
@@ -205,6 +223,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 const uint32_t as = kc % (uint32_t)p.a_stages, asph = (kc / (uint32_t)p.a_stages) & 1u;
                 mbar_wait(smem_u32(&bars->a_full[as]), asph);
                 tc_fence_after();
+                if (lane == 0 && t == (int)blockIdx.x && kb < 8) DP_TRACE(32 + kb);
                 const int kvalid = min(64, p.C - kb * 64);
                 const int nks = (kvalid + 15) >> 4;                     // 16-channel k-steps that hold data
                 const uint32_t ta_hi = tmem_a0 + as * 64u, ta_lo = ta_hi + 32u;
@@ -224,6 +243,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                         }
                         umma_commit(smem_u32(&bars->b_empty[bs]));
                         if (np == p.n_pass - 1) {
+                            if (t == (int)blockIdx.x && kb < 8) DP_TRACE(40 + kb);
                             umma_commit(smem_u32(&bars->a_empty[as]));
                             if (kb == p.nkb - 1) umma_commit(smem_u32(&bars->tmem_full[a]));
                         }
@@ -234,30 +254,44 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         }
     } else if (warp < 10) {
         // ================= depthwise: shared-memory window -> registers -> (hi, mid) bf16 planes in tensor memory =================
+        // Work unit = (8x4 block q, 16-channel half h of the k-block): thread (i = lane/4, m = lane%4) computes the 4 vertically
+        // adjacent pixels (x = i, y = 0..3) of ONE channel quad.  Under the weight k-permutation (gemm_tc.h d_bh_p) the tensor
+        // memory columns 8u + 2m (+1) of a 32-channel chunk hold channels 8m + 4u .. +3, i.e. thread m of half u reads quad
+        // 2m + u: the 8 lanes of a quarter warp touch all eight 16-byte chunks of their pixels' 128-byte lines (no bank conflict).
         const int q = warp & 3;            // TMEM lane quarter this warp may touch == the 8x4 block of the tile it computes
-        const int g = (warp - 2) >> 2;     // which 32-channel half of the k-block
+        const int hsel = (warp - 2) >> 2;  // this warp takes halves hsel and hsel + 2 of every k-block (= unit hsel of chunk 0 / 1)
         const int bx = q % p.tw, by = q / p.tw;
-        const int i = lane >> 2, qsel = lane & 3;
+        const int i = lane >> 2, m = lane & 3;
+        const int quad = 2 * m + hsel;     // channel quad inside a 32-channel chunk
         const int WC = p.win_cols;
+        const bool tracer = warp == 2 && lane == 0;
+        mbar_wait(smem_u32(&bars->par_full), 0u);
+        float4 w9[9];
+        auto load_taps = [&](int cbase) {
+            const float *wp = s_dw + cbase + quad * 4;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) w9[k] = *reinterpret_cast<const float4 *>(wp + k * p.cpad);
+        };
+        const bool hoist = p.nkb == 1 && p.C <= 32;   // one chunk per tile: the taps of this thread never change
+        if (hoist) load_taps(0);
         uint32_t wseq = 0, kc = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             for (int kb = 0; kb < p.nkb; ++kb, ++kc) {
                 const int nvalid = min(2, (p.C - kb * 64 + 31) >> 5);    // window chunks of this k-block
+                const int nhalf = min(4, (p.C - kb * 64 + 15) >> 4);     // 16-channel halves that hold data
                 const uint32_t as = kc % (uint32_t)p.a_stages, asph = (kc / (uint32_t)p.a_stages) & 1u;
-                if (g < nvalid) {
-                    const uint32_t seq = wseq + (uint32_t)g;
+                mbar_wait(smem_u32(&bars->a_empty[as]), asph ^ 1u);       // the MMAs that read this A stage have retired
+                tc_fence_after();
+                bool stored = false;
+                for (int ch = 0; ch < nvalid; ++ch) {
+                    const uint32_t seq = wseq + (uint32_t)ch;
                     const uint32_t s = seq % WIN_STAGES, ph = (seq / WIN_STAGES) & 1u;
                     mbar_wait(smem_u32(&bars->win_full[s]), ph);
-                    const uint32_t wbase = win_slot((int)s);
-                    const int cbase = kb * 64 + g * 32;
-                    uint32_t hi[2][8], lo[2][8];   // [lane half][registers of the 16x256b.x2 store]
-#pragma unroll
-                    for (int qi = 0; qi < 2; ++qi) {
-                        const int quad = qsel + 4 * qi;
-                        const float *wp = s_dw + cbase + quad * 4;
-                        float4 w9[9];
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) w9[k] = *reinterpret_cast<const float4 *>(wp + k * p.cpad);
+                    if (tracer && t == (int)blockIdx.x && kb < 8 && ch == 0) DP_TRACE(8 + kb);
+                    if (2 * ch + hsel < nhalf) {
+                        const uint32_t wbase = win_slot((int)s);
+                        const int cbase = kb * 64 + ch * 32;
+                        if (!hoist) load_taps(cbase);
                         float4 acc[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -283,53 +317,56 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                                 }
                             }
                         }
-                        const float4 sc = *reinterpret_cast<const float4 *>(wp + 9 * p.cpad);
-                        const float4 sh = *reinterpret_cast<const float4 *>(wp + 10 * p.cpad);
+                        const float *bnp = s_dw + 9 * p.cpad + cbase + quad * 4;
+                        const float4 sc = *reinterpret_cast<const float4 *>(bnp);
+                        const float4 sh = *reinterpret_cast<const float4 *>(bnp + p.cpad);
+                        const uint32_t ta = tmem_a0 + as * 64u + (uint32_t)(ch * 16 + hsel * 8);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float o0 = dw_act_f(fmaf(acc[j].x, sc.x, sh.x), p.dw_act, p.dw_alpha);
-                            const float o1 = dw_act_f(fmaf(acc[j].y, sc.y, sh.y), p.dw_act, p.dw_alpha);
-                            const float o2 = dw_act_f(fmaf(acc[j].z, sc.z, sh.z), p.dw_act, p.dw_alpha);
-                            const float o3 = dw_act_f(fmaf(acc[j].w, sc.w, sh.w), p.dw_act, p.dw_alpha);
-                            const uint32_t h01 = pack_bf16x2(o0, o1), h23 = pack_bf16x2(o2, o3);
-                            const float r0 = o0 - __uint_as_float(h01 << 16), r1 = o1 - __uint_as_float(h01 & 0xffff0000u);
-                            const float r2 = o2 - __uint_as_float(h23 << 16), r3 = o3 - __uint_as_float(h23 & 0xffff0000u);
-                            // pixel row j of the block = GEMM row i + 8j of the quarter: lane half j>>1, register pair (j&1)
-                            const int hf = j >> 1, rp = (j & 1) * 2 + qi * 4;
-                            hi[hf][rp] = h01;
-                            hi[hf][rp + 1] = h23;
-                            lo[hf][rp] = pack_bf16x2(r0, r1);
-                            lo[hf][rp + 1] = pack_bf16x2(r2, r3);
+                        for (int hf = 0; hf < 2; ++hf) {
+                            // pixel rows 2hf, 2hf+1 of the block = GEMM rows i + 8*(2hf), i + 8*(2hf+1) of the quarter: lane half hf
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj) {
+                                const int j = 2 * hf + jj;
+                                const float o0 = dw_act_f(fmaf(acc[j].x, sc.x, sh.x), p.dw_act, p.dw_alpha);
+                                const float o1 = dw_act_f(fmaf(acc[j].y, sc.y, sh.y), p.dw_act, p.dw_alpha);
+                                const float o2 = dw_act_f(fmaf(acc[j].z, sc.z, sh.z), p.dw_act, p.dw_alpha);
+                                const float o3 = dw_act_f(fmaf(acc[j].w, sc.w, sh.w), p.dw_act, p.dw_alpha);
+                                const uint32_t h01 = pack_bf16x2(o0, o1), h23 = pack_bf16x2(o2, o3);
+                                const float r0 = o0 - __uint_as_float(h01 << 16), r1 = o1 - __uint_as_float(h01 & 0xffff0000u);
+                                const float r2 = o2 - __uint_as_float(h23 << 16), r3 = o3 - __uint_as_float(h23 & 0xffff0000u);
+                                hi[jj * 2] = h01;
+                                hi[jj * 2 + 1] = h23;
+                                lo[jj * 2] = pack_bf16x2(r0, r1);
+                                lo[jj * 2 + 1] = pack_bf16x2(r2, r3);
+                            }
+                            const uint32_t lane_off = (uint32_t)(q * 32 + hf * 16) << 16;
+                            tmem_st_16x256b_x1(ta + lane_off, hi[0], hi[1], hi[2], hi[3]);
+                            tmem_st_16x256b_x1(ta + 32u + lane_off, lo[0], lo[1], lo[2], lo[3]);
                         }
+                        stored = true;
                     }
-                    // the window slot is free as soon as every lane has its values in registers
+                    // the window slot is free as soon as every lane has consumed its values
                     mbar_arrive(smem_u32(&bars->win_empty[s]));
-                    mbar_wait(smem_u32(&bars->a_empty[as]), asph ^ 1u);   // the MMAs that read this A stage have retired
-                    tc_fence_after();
-                    const uint32_t ta = tmem_a0 + as * 64u + (uint32_t)(g * 16);
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const uint32_t lane_off = (uint32_t)(q * 32 + hf * 16) << 16;
-                        tmem_st_16x256b_x2(ta + lane_off, hi[hf]);
-                        tmem_st_16x256b_x2(ta + 32u + lane_off, lo[hf]);
-                    }
-                    tmem_st_wait();
-                } else {
-                    mbar_wait(smem_u32(&bars->a_empty[as]), asph ^ 1u);
+                    if (tracer && t == (int)blockIdx.x && kb < 8 && ch == nvalid - 1) DP_TRACE(16 + kb);
                 }
+                if (stored) tmem_st_wait();
+                if (tracer && t == (int)blockIdx.x && kb < 8) DP_TRACE(24 + kb);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars->a_full[as]));
                 wseq += (uint32_t)nvalid;
             }
         }
     } else {
-        // ================= epilogue =================
+        // ================= epilogue: two warps per TMEM quarter, alternating 32-column chunks =================
         const int ew = warp - 10;
         const int q = warp & 3;
+        const int esel = ew >> 2;
         const int bx = q % p.tw, by = q / p.tw;
-        const uint32_t stg_base = smem_base + p.off_stage + (uint32_t)ew * 8192u;
+        const uint32_t stg_base = smem_base + p.off_stage + (uint32_t)ew * 4096u * (uint32_t)p.stg_bufs;
         const uint32_t ss = smem_base + p.off_ss;
         const uint32_t sh_off = (uint32_t)acc_cols * 4u;
+        const int n_lim = (p.N + 15) & ~15;
         uint32_t it = 0, stg_it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int b = t / tiles_per_img, r = t - b * tiles_per_img;
@@ -339,10 +376,11 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             const uint32_t a = it % (uint32_t)p.acc_stages, aph = (it / (uint32_t)p.acc_stages) & 1u;
             mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
             tc_fence_after();
+            if (ew == 0 && lane == 0 && t == (int)blockIdx.x) DP_TRACE(48);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)acc_cols;
-            for (int c0 = 0; c0 < acc_cols && c0 < ((p.N + 15) & ~15); c0 += 32, ++stg_it) {
+            for (int c0 = esel * 32; c0 < acc_cols && c0 < n_lim; c0 += 64, ++stg_it) {
                 const int ncols = (acc_cols - c0) < 32 ? (acc_cols - c0) : 32;   // 32 or 16
-                const uint32_t stg = stg_base + (stg_it & 1u) * 4096u;
+                const uint32_t stg = stg_base + (p.stg_bufs == 2 ? (stg_it & 1u) * 4096u : 0u);
                 uint32_t rr[32];
                 tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&rr[0]));
                 if (ncols == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&rr[16]));
@@ -351,21 +389,32 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     for (int j = 16; j < 32; ++j) rr[j] = 0u;
                 }
                 tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 s4 = ld_shared_v4(ss + (uint32_t)(c0 + j) * 4u);
-                    const float4 h4 = ld_shared_v4(ss + sh_off + (uint32_t)(c0 + j) * 4u);
-                    float v;
-                    v = fmaf(__uint_as_float(rr[j]), s4.x, h4.x);
-                    rr[j] = __float_as_uint(p.act == ACT_LEAKY ? fmaxf(v, v * p.act_slope) : dw_act_f(v, p.act, p.act_slope));
-                    v = fmaf(__uint_as_float(rr[j + 1]), s4.y, h4.y);
-                    rr[j + 1] = __float_as_uint(p.act == ACT_LEAKY ? fmaxf(v, v * p.act_slope) : dw_act_f(v, p.act, p.act_slope));
-                    v = fmaf(__uint_as_float(rr[j + 2]), s4.z, h4.z);
-                    rr[j + 2] = __float_as_uint(p.act == ACT_LEAKY ? fmaxf(v, v * p.act_slope) : dw_act_f(v, p.act, p.act_slope));
-                    v = fmaf(__uint_as_float(rr[j + 3]), s4.w, h4.w);
-                    rr[j + 3] = __float_as_uint(p.act == ACT_LEAKY ? fmaxf(v, v * p.act_slope) : dw_act_f(v, p.act, p.act_slope));
+                // folded BN + activation, specialised outside the element loop
+#define K2Y_DP_EPI(ACT_EXPR)                                                                                        \
+    _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                                             \
+        const float4 s4 = ld_shared_v4(ss + (uint32_t)(c0 + j) * 4u);                                               \
+        const float4 h4 = ld_shared_v4(ss + sh_off + (uint32_t)(c0 + j) * 4u);                                      \
+        float v;                                                                                                     \
+        v = fmaf(__uint_as_float(rr[j]), s4.x, h4.x);     rr[j] = __float_as_uint(ACT_EXPR);                         \
+        v = fmaf(__uint_as_float(rr[j + 1]), s4.y, h4.y); rr[j + 1] = __float_as_uint(ACT_EXPR);                     \
+        v = fmaf(__uint_as_float(rr[j + 2]), s4.z, h4.z); rr[j + 2] = __float_as_uint(ACT_EXPR);                     \
+        v = fmaf(__uint_as_float(rr[j + 3]), s4.w, h4.w); rr[j + 3] = __float_as_uint(ACT_EXPR);                     \
+    }
+                if (p.act == ACT_LEAKY) {
+                    const float slope = p.act_slope;
+                    K2Y_DP_EPI(fmaxf(v, v * slope))
+                } else if (p.act == ACT_RELU) {
+                    K2Y_DP_EPI(fmaxf(v, 0.f))
+                } else if (p.act == ACT_RELU6) {
+                    K2Y_DP_EPI(fminf(fmaxf(v, 0.f), 6.f))
+                } else {
+                    K2Y_DP_EPI(v)
                 }
-                if (lane == 0) tma_store_wait_read1();   // the staging buffer used two chunks ago has been read by its store
+#undef K2Y_DP_EPI
+                if (lane == 0) {   // the staging buffer about to be overwritten has been read by its store
+                    if (p.stg_bufs == 2) tma_store_wait_read1();
+                    else tma_store_wait_read0();
+                }
                 __syncwarp();
                 // lane = GEMM row i + 8j of the quarter = pixel (x = i, y = j) of the 8x4 block = row of the [y][x][32 ch] store box
 #pragma unroll
@@ -381,12 +430,15 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->tmem_empty[a]));
+            if (ew == 0 && lane == 0 && t == (int)blockIdx.x) DP_TRACE(49);
         }
         if (lane == 0) tma_store_wait_all();
+        if (ew == 0 && lane == 0) DP_TRACE(50);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) DP_TRACE(51);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -488,7 +540,10 @@ bool plan_dwpw(const DwArgs &dw, const ConvArgs &pw, int dev, DwPwPlan *out) {
     off += B_STAGES * 2u * (uint32_t)p.BN * 128u;
     off = (off + 1023u) & ~1023u;
     p.off_stage = off;
-    off += 4u * 8192u;
+    // staging: 8 epilogue warps, double-buffered against their TMA stores when shared memory allows
+    const uint32_t rest = ((uint32_t)(2 * acc) * 4u + 255u) / 256u * 256u + (11u * p.cpad * 4u + 255u) / 256u * 256u + (uint32_t)sizeof(DpBarriers) + 1024u;
+    p.stg_bufs = (size_t)off + 8u * 8192u + rest <= g_dp_smem[dev] ? 2 : 1;
+    off += 8u * 4096u * (uint32_t)p.stg_bufs;
     p.off_ss = off;
     off += ((uint32_t)(2 * acc) * 4u + 255u) & ~255u;
     p.off_dw = off;
@@ -518,11 +573,11 @@ int dp_init(int *dev_out) {
 
 // The MobileNet block `dw` (depthwise 3x3, stride 1, SAME) followed by the plain 1x1 conv `pw` reading exactly its output.
 bool dwpw_supported(const DwArgs &dw, const ConvArgs &pw, const TcWeights &w, int math_mode) {
-    if (math_mode != K2Y_MATH_TC_BF16X3 || !w.d_bh || !get_encode4()) return false;
+    if (math_mode != K2Y_MATH_TC_BF16X3 || !w.d_bh_p || !w.d_bm_p || !get_encode4()) return false;
     if (dw.stride != 1 || dw.pad_t != 1 || dw.pad_l != 1 || dw.OH != dw.H || dw.OW != dw.W) return false;
     if (pw.kh != 1 || pw.kw != 1 || pw.stride != 1 || pw.src1 || pw.up0 || pw.residual || pw.pad_t || pw.pad_l) return false;
     if (pw.src0 != dw.dst || pw.C0 != dw.C || pw.C1 != 0 || pw.OH != dw.OH || pw.OW != dw.OW || pw.B != dw.B) return false;
-    if ((dw.C & 3) || (pw.N & 3) || dw.C > 512 || pw.N > 384) return false;
+    if ((dw.C & 3) || (pw.N & 3) || dw.C > 512 || pw.N > 384 || !dw.pack || dw.cpad != (dw.C + 63) / 64 * 64) return false;
     if ((((uintptr_t)dw.src) & 15) || (((uintptr_t)pw.dst) & 15)) return false;
     int dev = 0;
     if (dp_init(&dev) != K2Y_OK) return false;
@@ -536,9 +591,7 @@ cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights
     DwPwPlan plan;
     if (!plan_dwpw(dw, pw, dev, &plan)) return cudaErrorInvalidConfiguration;
     DwPwParams &p = plan.p;
-    p.dw_w = dw.w;
-    p.dw_scale = dw.scale;
-    p.dw_shift = dw.shift;
+    p.dw_pack = dw.pack;
     p.dw_act = dw.act;
     p.dw_alpha = dw.alpha;
     p.scale = pw.scale;
@@ -548,8 +601,8 @@ cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights
     CUtensorMap map_in, map_bhi, map_blo, map_out;
     if (!make_map_nhwc(&map_in, dw.src, p.B, p.H, p.W, p.C, 32, p.win_cols, p.win_rows)) return cudaErrorInvalidValue;
     if (!make_map_nhwc(&map_out, pw.dst, p.B, p.H, p.W, p.N, 32, 8, 4)) return cudaErrorInvalidValue;
-    if (!make_map_weights(&map_bhi, w.d_bh, (uint64_t)w.Npad, (uint64_t)w.Kpad64, (uint32_t)p.BN)) return cudaErrorInvalidValue;
-    if (!make_map_weights(&map_blo, w.d_bm, (uint64_t)w.Npad, (uint64_t)w.Kpad64, (uint32_t)p.BN)) return cudaErrorInvalidValue;
+    if (!make_map_weights(&map_bhi, w.d_bh_p, (uint64_t)w.Npad, (uint64_t)w.Kpad64, (uint32_t)p.BN)) return cudaErrorInvalidValue;
+    if (!make_map_weights(&map_blo, w.d_bm_p, (uint64_t)w.Npad, (uint64_t)w.Kpad64, (uint32_t)p.BN)) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)plan.grid);
@@ -561,8 +614,34 @@ cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    p.trace = nullptr;
+    const char *tr = getenv("K2Y_TC_TRACE");
+    long long *d_trace = nullptr;
+    if (tr && tr[0] == '1') {
+        cudaMalloc(&d_trace, (size_t)plan.grid * 64 * sizeof(long long));
+        cudaMemset(d_trace, 0, (size_t)plan.grid * 64 * sizeof(long long));
+        p.trace = d_trace;
+        cfg.numAttrs = 0;
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, dwpw_tc_kernel, map_in, map_bhi, map_blo, map_out, p);
     if (e != cudaSuccess) return e;
+    if (d_trace) {
+        cudaStreamSynchronize(st);
+        long long h[64];
+        fprintf(stderr, "[dwpw-trace] %dx%d C=%d N=%d tile %dx%d tiles=%d grid=%d nkb=%d BN=%d n_pass=%d acc_stages=%d a_stages=%d smem=%zu\n", p.H, p.W,
+                p.C, p.N, 8 * p.tw, 4 * p.th, p.num_tiles, plan.grid, p.nkb, p.BN, p.n_pass, p.acc_stages, p.a_stages, plan.smem);
+        for (int cta : {0, plan.grid - 1}) {
+            cudaMemcpy(h, d_trace + (size_t)cta * 64, sizeof(h), cudaMemcpyDeviceToHost);
+            auto us = [&](int i) { return h[i] ? (h[i] - h[0]) * 1e-3 : -1.0; };
+            fprintf(stderr, "[dwpw-trace] cta %d: setup %.2f | win issue", cta, us(1));
+            for (int i = 0; i < 6; ++i) fprintf(stderr, " %.2f", us(2 + i));
+            fprintf(stderr, "\n[dwpw-trace]   kb: win_landed dw_computed tmem_stored | mma_got_A mma_issued\n");
+            for (int kb = 0; kb < p.nkb && kb < 8; ++kb)
+                fprintf(stderr, "[dwpw-trace]   %d: %.2f %.2f %.2f | %.2f %.2f\n", kb, us(8 + kb), us(16 + kb), us(24 + kb), us(32 + kb), us(40 + kb));
+            fprintf(stderr, "[dwpw-trace]   epilogue: acc ready %.2f, tile done %.2f, stores drained %.2f, cta end %.2f\n", us(48), us(49), us(50), us(51));
+        }
+        cudaFree(d_trace);
+    }
     return cudaGetLastError();
 }
 

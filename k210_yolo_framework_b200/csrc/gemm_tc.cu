@@ -922,7 +922,7 @@ int tc_init() {
 
 }  // namespace
 
-int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N) {
+int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N, bool with_permuted) {
     tc_free(w);
     int rc = tc_init();
     if (rc != K2Y_OK) return rc;
@@ -956,6 +956,23 @@ int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N) {
     K2Y_CUDA_CHECK(cudaMalloc(&w.d_bm, bm.size() * sizeof(uint16_t)));
     K2Y_CUDA_CHECK(cudaMemcpy(w.d_bh, bh.data(), bh.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     K2Y_CUDA_CHECK(cudaMemcpy(w.d_bm, bm.data(), bm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if (with_permuted) {
+        std::vector<uint16_t> ph((size_t)w.Npad * w.Kpad64, 0), pm((size_t)w.Npad * w.Kpad64, 0);
+        for (int kp = 0; kp < w.Kpad64; ++kp) {
+            const int base = kp & ~31, kap = kp & 31;
+            const int u = kap >> 4, m = (kap >> 2) & 3, e = kap & 3;
+            const int k = base + 8 * m + 4 * u + e;   // the channel stored at k position kp
+            if (k >= K) continue;
+            for (int n = 0; n < N; ++n) {
+                ph[(size_t)n * w.Kpad64 + kp] = bh[(size_t)n * w.Kpad64 + k];
+                pm[(size_t)n * w.Kpad64 + kp] = bm[(size_t)n * w.Kpad64 + k];
+            }
+        }
+        K2Y_CUDA_CHECK(cudaMalloc(&w.d_bh_p, ph.size() * sizeof(uint16_t)));
+        K2Y_CUDA_CHECK(cudaMalloc(&w.d_bm_p, pm.size() * sizeof(uint16_t)));
+        K2Y_CUDA_CHECK(cudaMemcpy(w.d_bh_p, ph.data(), ph.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        K2Y_CUDA_CHECK(cudaMemcpy(w.d_bm_p, pm.data(), pm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     return K2Y_OK;
 }
 
@@ -964,6 +981,8 @@ void tc_free(TcWeights &w) {
     cudaFree(w.d_lo);
     cudaFree(w.d_bh);
     cudaFree(w.d_bm);
+    cudaFree(w.d_bh_p);
+    cudaFree(w.d_bm_p);
     w = TcWeights();
 }
 

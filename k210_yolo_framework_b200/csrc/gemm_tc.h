@@ -11,10 +11,14 @@ struct TcWeights {
     float *d_lo = nullptr;
     unsigned short *d_bh = nullptr;  // bf16x3: bf16(w) and bf16(w - hi) planes, K-major [Npad][Kpad64]
     unsigned short *d_bm = nullptr;
+    // the same two planes with the k index permuted inside every 32-channel chunk (k = 16u + 4m + e holds channel 8m + 4u + e):
+    // the order in which the fused depthwise producer (dwpw_tc.cu) lays channels out in tensor memory; 1x1 convs only
+    unsigned short *d_bh_p = nullptr;
+    unsigned short *d_bm_p = nullptr;
     int K = 0, N = 0, Kpad = 0, Kpad64 = 0, Npad = 0;
 };
 
-int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N);  // kernel_kn: [K][N] row-major (Keras HWIO flattened)
+int tc_pack(TcWeights &w, const float *kernel_kn, int K, int N, bool with_permuted = false);  // kernel_kn: [K][N] row-major (Keras HWIO flattened)
 void tc_free(TcWeights &w);
 bool tc_supported(const ConvArgs &a, const TcWeights &w);
 size_t tc_scratch_bound(const ConvArgs &a, const TcWeights &w);           // split-K scratch a net must provide for this layer

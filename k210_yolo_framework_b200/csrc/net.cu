@@ -4,6 +4,7 @@
 // keras_mobilenet.py:215-229,291-436), :49-104 (yolo_mobilev2 over keras_mobilenet_v2.py:311-382,
 // 426-485), :107-158 (tiny_yolo) and :161-229 (yolo / Darknet-53) as a static layer schedule.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -63,6 +64,8 @@ struct Layer {
     TcWeights tc2;
     float *d_scale2 = nullptr, *d_shift2 = nullptr;
     TcWeights tc;  // tensor-core packing (gemm_tc.cu)
+    float *d_dwpack = nullptr;  // depthwise layers: [11][cpad] taps + folded BN, zero-padded (DwArgs::pack)
+    int dw_cpad = 0;
     int fused = 0;  // last issue_layers(): 1 = this depthwise ran fused with the next 1x1 conv, 2 = this conv ran inside the previous launch
 };
 
@@ -456,8 +459,15 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
         return a;
     };
     int dw_ordinal = 0;
+    // one NVTX range per layer (header-only NVTX 3: a no-op unless a tool is attached); under graph capture the ranges
+    // bracket the capture-time issue of each node, in eager mode (k2y_net_set_use_graph(0), k2y_net_profile) the launches
+    struct NvtxRange {
+        explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+        ~NvtxRange() { nvtxRangePop(); }
+    };
     for (size_t idx = 0; idx < n->layers.size(); ++idx) {
         Layer &L = n->layers[idx];
+        NvtxRange range(L.name.c_str());
         L.fused = 0;
         const Tensor &s0 = n->tensors[L.src0];
         const Tensor &d = n->tensors[L.dst];
@@ -512,6 +522,8 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
             a.pad_l = L.pad_l;
             a.act = L.act;
             a.alpha = L.alpha;
+            a.pack = L.d_dwpack;
+            a.cpad = L.dw_cpad;
             // optional (K2Y_DWPW_FUSION=1): depthwise + the following 1x1 conv as one tensor-core launch, the depthwise output
             // goes straight into the GEMM's A stage (skipped when every layer output must be readable)
             bool fused = false;
@@ -649,7 +661,8 @@ extern "C" int k2y_net_destroy(k2y_net *net) {
         tc_free(L.tc2);
         cudaFree(L.d_scale2);
         cudaFree(L.d_shift2);
-        L.d_scale2 = L.d_shift2 = nullptr;
+        cudaFree(L.d_dwpack);
+        L.d_scale2 = L.d_shift2 = L.d_dwpack = nullptr;
     }
     delete net;
     return K2Y_OK;
@@ -783,8 +796,24 @@ extern "C" int k2y_net_finalize(k2y_net *net) {
         K2Y_CUDA_CHECK(cudaMemcpy(L.d_shift, shift.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
         L.h_scale = scale;
         L.h_shift = shift;
+        if (L.kind == L_DW) {
+            const int C = L.cout, cpad = (C + 63) / 64 * 64;
+            std::vector<float> pack((size_t)11 * cpad, 0.f);
+            for (int c = 0; c < C; ++c) {
+                for (int t = 0; t < 9; ++t) pack[(size_t)t * cpad + c] = L.kernel[(size_t)t * C + c];
+                pack[(size_t)9 * cpad + c] = scale[c];
+                pack[(size_t)10 * cpad + c] = shift[c];
+            }
+            cudaFree(L.d_dwpack);
+            L.d_dwpack = nullptr;
+            K2Y_CUDA_CHECK(cudaMalloc(&L.d_dwpack, pack.size() * sizeof(float)));
+            K2Y_CUDA_CHECK(cudaMemcpy(L.d_dwpack, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice));
+            L.dw_cpad = cpad;
+        }
         if (L.kind == L_CONV) {
-            int rc = tc_pack(L.tc, L.kernel.data(), L.kh * L.kw * L.cin, L.cout);
+            // 1x1 convs behind a depthwise layer also get the k-permuted planes of the fused kernel
+            const bool after_dw = L.kh == 1 && L.src0 >= 0 && net->tensors[L.src0].def >= 0 && net->layers[net->tensors[L.src0].def].kind == L_DW;
+            int rc = tc_pack(L.tc, L.kernel.data(), L.kh * L.kw * L.cin, L.cout, after_dw);
             if (rc != K2Y_OK) return rc;
             tc_free(L.tc2);
             cudaFree(L.d_scale2);

@@ -91,3 +91,21 @@ if __name__ == "__main__":
     if "--people-only" not in sys.argv:
         main()
     people_golden()
+
+
+def label_boxes_of_reference_render():
+    """Geometry of the filled label boxes in the reference's own rendered result (asset/dog_res.jpg, drawn by
+    keras_inference.py:137-174): per class, the bounding rows / columns of the pixels close to the class colour.  The 1-px
+    rectangle outlines do not survive the JPEG compression, the filled label boxes do.  -> tests/golden/dog_res_labels.json"""
+    import json
+    from PIL import Image
+    from k210_yolo_framework_b200.helper import _COLORMAP
+    im = np.array(Image.open("/root/reference/asset/dog_res.jpg").convert("RGB")).astype(int)
+    out = {}
+    for c in (6, 11):
+        d = np.abs(im - np.array(_COLORMAP[c])).sum(-1)
+        ys, xs = np.nonzero(d < 60)
+        out[str(c)] = {"ymin": int(ys.min()), "ymax": int(ys.max()), "xmin": int(xs.min()), "xmax": int(xs.max()), "pixels": int(len(ys))}
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "dog_res_labels.json"), "w") as fh:
+        json.dump(out, fh)
+    return out
