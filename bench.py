@@ -297,6 +297,19 @@ def run_ours(args, cfg):
         pipe.engine.bind_input(xs[i % n_in])
         pipe.step_device()
     barrier()
+    if args.profile_step:
+        # `ncu --profile-from-start off ... bench.py --profile-step`: exactly ONE step between cudaProfilerStart/Stop, cold input
+        names = [a["name"] for a in pipe.engine.profile(B)]
+        pipe.engine.bind_input(xs[(args.warmup + 1) % n_in])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        pipe.step_device()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        if rank == 0:
+            emit(json.dumps({"profile_step": True, "config": workload_config(cfg, world), "schedule": names,
+                             "launches_per_step": pipe.launches_per_step()}))
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -505,6 +518,7 @@ def main():
                     help="BASELINE.json config: 2 yolo_mobilev1-0.75 (default, the headline), 3 tiny_yolo 416, 4 yolo_mobilev2, 5 Darknet-53 608")
     ap.add_argument("--math", choices=["fp32_simt", "tc_3xtf32", "tc_tf32", "tc_bf16x3"], default=os.environ.get("K2Y_BENCH_MATH", "tc_bf16x3"))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs (profiling runs)")
+    ap.add_argument("--profile-step", action="store_true", help="warm up, then run exactly one step between cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = wl.CONFIGS[args.config]

@@ -31,7 +31,10 @@ void set_error(const char *fmt, ...) {
 
 namespace {
 
-constexpr bool DWPW_DEFAULT_ON = false;  // fused depthwise->pointwise blocks in the default schedule (K2Y_DWPW=1 / K2Y_NO_DWPW=1 override)
+constexpr bool DWPW_DEFAULT_ON = true;   // fused depthwise->pointwise blocks in the default schedule (K2Y_NO_DWPW=1 disables)
+constexpr int DWPW_DEFAULT_MAX_C = 96;   // ... for blocks of at most this many channels: the HBM-bound early blocks, where the fused
+                                         // launch measured faster than the pair (profiles/r02_dwpw_fusion.md); K2Y_DWPW=1 fuses every
+                                         // supported block
 constexpr float BN_EPS = 1e-3f;  // Keras BatchNormalization epsilon used by every reference model
 
 enum LayerKind { L_CONV = 0, L_DW = 1, L_POOL = 2 };
@@ -536,7 +539,8 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
                     // default schedule: stride-1 blocks run as ONE launch (dwpw_tc.cu).  K2Y_NO_DWPW=1 disables it,
                     // K2Y_DWPW_MASK=<bitmask over the depthwise layers in schedule order> restricts it (per-layer measurements).
                     const char *no = getenv("K2Y_NO_DWPW"), *yes = getenv("K2Y_DWPW"), *mask = getenv("K2Y_DWPW_MASK");
-                    const bool on = DWPW_DEFAULT_ON ? !(no && no[0] == '1') : (yes && yes[0] == '1');
+                    const bool force = yes && yes[0] == '1';
+                    const bool on = force || (DWPW_DEFAULT_ON && !(no && no[0] == '1') && a.C <= DWPW_DEFAULT_MAX_C);
                     const bool allowed = on && (!mask || ((strtoul(mask, nullptr, 0) >> (dw_ordinal - 1)) & 1ul));
                     if (allowed && dwpw_supported(a, pa, P.tc, n->math)) {
                         e = launch_dwpw_tc(a, pa, P.tc, st);

@@ -146,6 +146,12 @@ def test_fused_depthwise_pointwise_blocks(monkeypatch):
         for p, q in zip(one, plain):
             assert torch.allclose(p, q, atol=3e-4, rtol=1e-4), (blk, float((p - q).abs().max()))
     monkeypatch.delenv("K2Y_DWPW_MASK")
+    # the default schedule fuses the HBM-bound early blocks only (C <= 96), where the single launch measured faster
+    monkeypatch.delenv("K2Y_DWPW")
+    m.predict_device(x)
+    dflt = [p["name"] for p in m.engine.profile(3) if "+" in p["name"]]
+    assert dflt == ["conv_dw_1+conv_pw_1", "conv_dw_3+conv_pw_3"], dflt
+    monkeypatch.setenv("K2Y_DWPW", "1")
     # against the oracle, on extents where tiles are partial (96x160 -> 48x80, 24x40, 12x20, 6x10 maps) and C = 16..512
     for alpha, hw in ((0.5, (96, 160)), (1.0, (64, 96))):
         m2, _ = yolonet.yolo_mobilev1([hw[0], hw[1], 3], 3, 20, alpha=alpha, max_batch=2)
