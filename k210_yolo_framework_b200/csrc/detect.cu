@@ -266,7 +266,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
         const float *src = p.heads[l] + ((size_t)b * (p.loff[l + 1] - p.loff[l]) + (lo - p.loff[l])) * E;
         float *dst = s_rec + (lo - box0) * E;
         const int cnt = (hi - lo) * E;
-        for (int i = tid; i < cnt; i += SCAN_THREADS) dst[i] = __ldg(src + i);
+        // four loads in flight per thread before the first store: the slab is cold (HBM / L2), a load-store-load chain would
+        // pay the full latency once per element
+        for (int i0 = 0; i0 < cnt; i0 += 4 * SCAN_THREADS) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * SCAN_THREADS + tid;
+                v[u] = i < cnt ? __ldg(src + i) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * SCAN_THREADS + tid;
+                if (i < cnt) dst[i] = v[u];
+            }
+        }
     }
     __syncthreads();
     if (tid < nb) {
@@ -281,17 +295,37 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
     }
     __syncthreads();
     const bool shortcut = p.logit_min > -__int_as_float(0x7f800000);
-    for (int it = tid; it < nb * p.C; it += SCAN_THREADS) {
-        const int i = it / p.C, c = it - i * p.C;
-        const float sc = s_conf[i];
-        if (shortcut && !(sc >= p.obj)) continue;
-        const float t = s_rec[i * E + 5 + c];
-        if (t < p.logit_min) continue;
-        const float s = __fmul_rn(sigmoidf_ref(t), sc);
-        if (s >= p.obj) {
-            const int pos = atomicAdd(p.ncand + b * p.C + c, 1);
-            p.keys[((size_t)b * p.C + c) * p.P + pos] = pack_key(s, box0 + i);
+    // (box, class) pairs, four per thread at a time: scores first, then the list-slot atomics back to back (independent, so
+    // their L2 round trips overlap), then the keys
+    for (int it0 = 0; it0 < nb * p.C; it0 += 4 * SCAN_THREADS) {
+        float sc4[4];
+        int cls[4], bi[4];
+        bool pass[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * SCAN_THREADS + tid;
+            pass[u] = false;
+            sc4[u] = 0.f;
+            cls[u] = bi[u] = 0;
+            if (it < nb * p.C) {
+                const int i = it / p.C, c = it - i * p.C;
+                const float sc = s_conf[i];
+                const float t = s_rec[i * E + 5 + c];
+                if ((!shortcut || sc >= p.obj) && !(t < p.logit_min)) {
+                    const float s = __fmul_rn(sigmoidf_ref(t), sc);
+                    pass[u] = s >= p.obj;
+                    sc4[u] = s;
+                    cls[u] = c;
+                    bi[u] = box0 + i;
+                }
+            }
         }
+        int pos[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pos[u] = pass[u] ? atomicAdd(p.ncand + b * p.C + cls[u], 1) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pass[u]) p.keys[((size_t)b * p.C + cls[u]) * p.P + pos[u]] = pack_key(sc4[u], bi[u]);
     }
 }
 
@@ -302,7 +336,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
 // warp-reduce instructions on the (score bits, ~index, position) triple + one shared-memory exchange) followed by one
 // IoU test per live candidate, all candidates spread over the CTA's threads.  The selection order is exactly the order of
 // the sorted keys (score descending, index ascending), so the records equal the sequential algorithm's.
-constexpr int NMS_THREADS = 256;
+constexpr int NMS_THREADS = 512;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
 
 __device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long long key, const float4 kb) {
@@ -334,22 +368,22 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
         }
     }
     int nsel = 0, par = 0;
-    while (nsel < p.maxk) {
-        // ---- best live candidate of this thread ----
-        unsigned long long best = 0ull;
-        int bpos = -1;
-        for (int w = 0; w < (SMEM ? 1 : nwords); ++w) {
-            for (unsigned m = SMEM ? mask0 : alive_g[(size_t)w * NMS_THREADS + tid]; m;) {
-                const int q = __ffs(m) - 1;
-                m &= m - 1u;
-                const int pos = tid + (w * 32 + q) * NMS_THREADS;
-                const unsigned long long k = keys[pos];
-                if (bpos < 0 || k > best) {
-                    best = k;
-                    bpos = pos;
-                }
+    // best live candidate of this thread; afterwards maintained by the kill pass of each round
+    unsigned long long best = 0ull;
+    int bpos = -1;
+    for (int w = 0; w < (SMEM ? 1 : nwords); ++w) {
+        for (unsigned m = SMEM ? mask0 : alive_g[(size_t)w * NMS_THREADS + tid]; m;) {
+            const int q = __ffs(m) - 1;
+            m &= m - 1u;
+            const int pos = tid + (w * 32 + q) * NMS_THREADS;
+            const unsigned long long k = keys[pos];
+            if (bpos < 0 || k > best) {
+                best = k;
+                bpos = pos;
             }
         }
+    }
+    while (nsel < p.maxk) {
         // ---- arg-max over the CTA: (score bits, ~index) lexicographic; keys are unique, so the winner is ----
         const unsigned hi = bpos >= 0 ? (unsigned)(best >> 32) : 0u;
         const unsigned mhi = __reduce_max_sync(FULL, hi);
@@ -363,17 +397,17 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
             s_red[par][warp][2] = mpos;
         }
         __syncthreads();
+        // every warp reduces the per-warp winners again (lane w holds warp w's entry): no second barrier needed
         unsigned whi = 0u, wlo = 0u;
         int wpos = 0x7fffffff;
-#pragma unroll
-        for (int w = 0; w < NMS_WARPS; ++w) {
-            const unsigned h2 = (unsigned)s_red[par][w][0], l2 = (unsigned)s_red[par][w][1];
-            const int p2 = s_red[par][w][2];
-            if (p2 != 0x7fffffff && (wpos == 0x7fffffff || h2 > whi || (h2 == whi && l2 > wlo))) {
-                whi = h2;
-                wlo = l2;
-                wpos = p2;
-            }
+        {
+            const int ent = lane < NMS_WARPS ? lane : 0;
+            const int p2 = lane < NMS_WARPS ? s_red[par][ent][2] : 0x7fffffff;
+            const unsigned h2 = p2 != 0x7fffffff ? (unsigned)s_red[par][ent][0] : 0u;
+            const unsigned l2 = p2 != 0x7fffffff ? (unsigned)s_red[par][ent][1] : 0u;
+            whi = __reduce_max_sync(FULL, h2);
+            wlo = __reduce_max_sync(FULL, (p2 != 0x7fffffff && h2 == whi) ? l2 : 0u);
+            wpos = __reduce_min_sync(FULL, (p2 != 0x7fffffff && h2 == whi && l2 == wlo) ? p2 : 0x7fffffff);
         }
         par ^= 1;
         if (wpos == 0x7fffffff) break;   // nothing alive
@@ -387,7 +421,9 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
             kb = norm_box(gboxes[key_index(wkey)], ka);
         }
         if (tid == 0) write_det(out, nsel, wkey, gboxes[key_index(wkey)]);
-        // ---- the kept box kills what it overlaps (and itself) ----
+        // ---- the kept box kills what it overlaps (and itself); the same pass finds this thread's best survivor ----
+        best = 0ull;
+        bpos = -1;
         for (int w = 0; w < (SMEM ? 1 : nwords); ++w) {
             unsigned word = SMEM ? mask0 : alive_g[(size_t)w * NMS_THREADS + tid];
             for (unsigned m = word; m;) {
@@ -395,16 +431,22 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
                 m &= m - 1u;
                 const int pos = tid + (w * 32 + q) * NMS_THREADS;
                 bool kill = pos == wpos;
+                const unsigned long long k = keys[pos];
                 if (!kill) {
                     if (SMEM) {
                         kill = iou_norm_gt(kb, ka, s_box[pos], s_area[pos], p.iou);
                     } else {
                         float ar;
-                        const float4 cb = norm_box(gboxes[key_index(keys[pos])], ar);
+                        const float4 cb = norm_box(gboxes[key_index(k)], ar);
                         kill = iou_norm_gt(kb, ka, cb, ar, p.iou);
                     }
                 }
-                if (kill) word &= ~(1u << q);
+                if (kill) {
+                    word &= ~(1u << q);
+                } else if (bpos < 0 || k > best) {
+                    best = k;
+                    bpos = pos;
+                }
             }
             if (SMEM) mask0 = word;
             else alive_g[(size_t)w * NMS_THREADS + tid] = word;
@@ -695,7 +737,7 @@ DetectLayout detect_layout(const k2y_detect_cfg *cfg, int batch) {
     L.nbox = 0;
     for (int l = 0; l < cfg->n_layers; ++l) L.nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
     L.P = (size_t)next_pow2((int)L.nbox);
-    L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 255) / 256 * 256) : (size_t)NMS_SMEM_CAP);
+    L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 511) / 512 * 512) : (size_t)NMS_SMEM_CAP);
     const size_t BC = (size_t)batch * cfg->class_num;
     size_t off = 256;  // alignment slack
     L.boxes_off = off;
