@@ -163,6 +163,7 @@ struct KerasParams {
     float in_h, in_w;
     float obj, iou;
     float logit_min;                  // a logit below this cannot give a sigmoid >= obj (with a wide margin); -inf = no shortcut
+    unsigned c_magic;                 // ceil(2^32 / C): it / C == __umulhi(it, c_magic) for the item counts of one slab
     int maxk;
     const float *image_hw;
     k2y_det *dets;
@@ -283,11 +284,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
         }
     }
     __syncthreads();
+    float *s_thr = s_conf + SCAN_BOXES;
     if (tid < nb) {
         // sigmoid(conf) once per box; score = sigmoid(cls) * sigmoid(conf) <= sigmoid(conf), so a box whose objectness is
-        // below the threshold has no candidate in any class (0 marks it: obj > 0 whenever the shortcut is on)
+        // below the threshold has no candidate in any class (0 marks it: obj > 0 whenever the shortcut is on).
+        // For the other boxes a class can only pass if sigmoid(cls) >= obj / sigmoid(conf), i.e. cls >= logit(obj / sc): a
+        // per-box logit bound (with a margin of 2e-3 (+0.2 %), thousands of float ulps of the sigmoid) rejects most
+        // (box, class) pairs with ONE comparison instead of a correctly rounded exponential.
         const float t = s_rec[tid * E + 4];
-        s_conf[tid] = (t < p.logit_min) ? 0.f : sigmoidf_ref(t);
+        const float sc = (t < p.logit_min) ? 0.f : sigmoidf_ref(t);
+        s_conf[tid] = sc;
+        float thr = p.logit_min;
+        if (p.logit_min > -__int_as_float(0x7f800000) && sc >= p.obj) {
+            const float q = __fdividef(p.obj, sc);
+            if (q < 0.999f) {   // 1 - q >= 1e-3: the margin below is > 1e-5 of the sigmoid, the float roundings involved < 1e-6
+                const float lg = __logf(__fdividef(q, 1.0f - q));
+                thr = fmaxf(thr, lg - 2e-3f - 2e-3f * fabsf(lg));
+            }
+        }
+        s_thr[tid] = thr;
     } else if (tid >= SCAN_BOXES && tid < SCAN_BOXES + nb) {
         const int i = tid - SCAN_BOXES;
         const BoxXform x = make_xform(p, b);
@@ -297,7 +312,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
     const bool shortcut = p.logit_min > -__int_as_float(0x7f800000);
     // (box, class) pairs, four per thread at a time: scores first, then the list-slot atomics back to back (independent, so
     // their L2 round trips overlap), then the keys
-    for (int it0 = 0; it0 < nb * p.C; it0 += 4 * SCAN_THREADS) {
+    const int n_items = nb * p.C;
+    for (int it0 = 0; it0 < n_items; it0 += 4 * SCAN_THREADS) {
         float sc4[4];
         int cls[4], bi[4];
         bool pass[4];
@@ -307,16 +323,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
             pass[u] = false;
             sc4[u] = 0.f;
             cls[u] = bi[u] = 0;
-            if (it < nb * p.C) {
-                const int i = it / p.C, c = it - i * p.C;
-                const float sc = s_conf[i];
+            if (it < n_items) {
+                const int i = (int)__umulhi((unsigned)it, p.c_magic), c = it - i * p.C;
                 const float t = s_rec[i * E + 5 + c];
-                if ((!shortcut || sc >= p.obj) && !(t < p.logit_min)) {
-                    const float s = __fmul_rn(sigmoidf_ref(t), sc);
-                    pass[u] = s >= p.obj;
-                    sc4[u] = s;
-                    cls[u] = c;
-                    bi[u] = box0 + i;
+                if (!(t < s_thr[i])) {
+                    const float sc = s_conf[i];
+                    if (!shortcut || sc >= p.obj) {
+                        const float s = __fmul_rn(sigmoidf_ref(t), sc);
+                        pass[u] = s >= p.obj;
+                        sc4[u] = s;
+                        cls[u] = c;
+                        bi[u] = box0 + i;
+                    }
                 }
             }
         }
@@ -456,9 +474,87 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
     return nsel;
 }
 
+// Shared-memory path (n <= cap <= 4096): every thread keeps its candidates (position pos = tid + s * NMS_THREADS) in registers —
+// packed key, (min,max)-normalised box, area.  The packed key is (score bits << 32) | ((0xFFFFF - index) << 12) | pos: the low
+// 12 bits never decide a comparison (the (score, index) pair is unique), so ONE 64-bit maximum yields the winner and where its
+// box sits in shared memory.  A round: per-warp maximum (two warp-reduce instructions) -> one shared-memory atomicMax per
+// warp -> barrier -> everybody reads the winner and its box -> IoU tests of the own (register) candidates, unrolled.
+template <int SLOTS>
+__device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, const unsigned long long *s_keys, const float4 *s_box,
+                                               const float *s_area, const float4 *gboxes, k2y_det *out, unsigned long long *s_best) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    unsigned long long pk[SLOTS];
+    float4 bx[SLOTS];
+    float ar[SLOTS];
+    unsigned alive = 0u;
+    unsigned long long tbest = 0ull;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int pos = tid + s * NMS_THREADS;
+        pk[s] = 0ull;
+        bx[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ar[s] = 0.f;
+        if (pos < n) {
+            const unsigned long long k = s_keys[pos];
+            // (score, ~index) -> (score, 20-bit ~index, 12-bit position); + 1 in the position field keeps the key non-zero
+            pk[s] = (k & 0xffffffff00000000ull) | ((unsigned long long)(0xFFFFFu - (unsigned)key_index(k)) << 12) | (unsigned long long)pos;
+            bx[s] = s_box[pos];
+            ar[s] = s_area[pos];
+            alive |= 1u << s;
+            tbest = pk[s] > tbest ? pk[s] : tbest;
+        }
+    }
+    if (tid < 3) s_best[tid] = 0ull;
+    __syncthreads();
+    int nsel = 0, slot = 0;
+    while (nsel < p.maxk) {
+        if (__ballot_sync(FULL, alive != 0u) != 0u) {   // warps whose candidates are all dead only keep the barrier company
+            const unsigned hi = (unsigned)(tbest >> 32);
+            const unsigned mhi = __reduce_max_sync(FULL, hi);
+            const unsigned lo = (alive != 0u && hi == mhi) ? (unsigned)tbest : 0u;
+            const unsigned mlo = __reduce_max_sync(FULL, lo);
+            if (lane == 0) atomicMax(&s_best[slot], ((unsigned long long)mhi << 32) | mlo);
+        }
+        __syncthreads();
+        const unsigned long long w = s_best[slot];
+        if (tid == 0) s_best[slot == 0 ? 2 : slot - 1] = 0ull;   // the slot used in the previous round is free again after this barrier...
+        slot = slot == 2 ? 0 : slot + 1;                          // ...and is written next in the round after the next one
+        if (w == 0ull) break;   // nothing alive (a live key is never 0: its score or its index field is non-zero ... or position)
+        const int wpos = (int)(w & 0xFFFull);
+        const float4 kb = s_box[wpos];
+        const float ka = s_area[wpos];
+        if (tid == 0) {
+            const int index = (int)(0xFFFFFu - (unsigned)((w >> 12) & 0xFFFFFull));
+            k2y_det d;
+            const float4 ob = gboxes[index];
+            d.ymin = ob.x;
+            d.xmin = ob.y;
+            d.ymax = ob.z;
+            d.xmax = ob.w;
+            d.score = __uint_as_float((unsigned)(w >> 32));
+            d.index = index;
+            out[nsel] = d;
+        }
+        tbest = 0ull;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            if ((alive >> s) & 1u) {
+                if (pk[s] == w || iou_norm_gt(kb, ka, bx[s], ar[s], p.iou)) alive &= ~(1u << s);
+                else tbest = pk[s] > tbest ? pk[s] : tbest;
+            }
+        }
+        ++nsel;
+    }
+    return nsel;
+}
+
+// SLOTS = candidates per thread of the shared-memory path (cap / NMS_THREADS rounded up to 2, 4 or 8): one kernel per value so
+// that the small grids (1050 boxes -> 3 candidates per thread) are not compiled at the register count of the largest
+template <int SLOTS>
 __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasParams p) {
     extern __shared__ __align__(16) unsigned char s_nms[];
     __shared__ int s_red[2][NMS_WARPS][3];
+    __shared__ unsigned long long s_best[3];
     pdl_trigger();
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
@@ -517,7 +613,7 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
             s_area[i] = ar;
         }
         __syncthreads();
-        nsel = nms_rounds<true>(p, n, s_keys, s_box, s_area, gboxes, nullptr, out, s_red);
+        nsel = nms_rounds_smem<SLOTS>(p, n, s_keys, s_box, s_area, gboxes, out, s_best);
     } else {
         unsigned *alive_g = p.alive + ((size_t)b * p.C + c) * (size_t)(p.P >> 5);
         nsel = nms_rounds<false>(p, n, gkeys, nullptr, nullptr, gboxes, alive_g, out, s_red);
@@ -738,6 +834,7 @@ DetectLayout detect_layout(const k2y_detect_cfg *cfg, int batch) {
     for (int l = 0; l < cfg->n_layers; ++l) L.nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
     L.P = (size_t)next_pow2((int)L.nbox);
     L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 511) / 512 * 512) : (size_t)NMS_SMEM_CAP);
+    if (L.nbox >= 0xFFFFFu) L.cap = 0;  // the shared-memory path packs the box index into 20 bits of its sort key
     const size_t BC = (size_t)batch * cfg->class_num;
     size_t off = 256;  // alignment slack
     L.boxes_off = off;
@@ -834,13 +931,16 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     p.ncand = reinterpret_cast<int *>(ws + L.ncand_off);
     p.alive = reinterpret_cast<unsigned *>(ws + L.alive_off);
     p.cap = L.cap;
-    const size_t scan_smem = (size_t)SCAN_BOXES * (5 + p.C + 1) * sizeof(float);
+    const size_t scan_smem = (size_t)SCAN_BOXES * (5 + p.C + 2) * sizeof(float);
+    p.c_magic = (unsigned)((0x100000000ull + (unsigned long long)p.C - 1ull) / (unsigned long long)p.C);
     const size_t nms_smem = (size_t)p.cap * 28;  // keys + boxes + areas
     int dev = 0;
     K2Y_CUDA_CHECK(cudaGetDevice(&dev));
     static bool attr_set[64] = {false};  // per device: opt-in shared memory is a per-device function attribute
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
         K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set[dev] = true;
     }
@@ -853,7 +953,9 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     dim3 sgrid((p.nbox + SCAN_BOXES - 1) / SCAN_BOXES, batch);
     detect_scan_kernel<<<sgrid, SCAN_THREADS, scan_smem, st>>>(p);  // follows a memset: plain stream order
     K2Y_CUDA_CHECK(cudaGetLastError());
-    launch_k(detect_nms_kernel, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
+    if (p.cap <= 2 * NMS_THREADS) launch_k(detect_nms_kernel<2>, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
+    else if (p.cap <= 4 * NMS_THREADS) launch_k(detect_nms_kernel<4>, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
+    else launch_k(detect_nms_kernel<8>, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
     K2Y_CUDA_CHECK(cudaGetLastError());
     return K2Y_OK;
 }

@@ -288,6 +288,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     const uint32_t s = seq % WIN_STAGES, ph = (seq / WIN_STAGES) & 1u;
                     mbar_wait(smem_u32(&bars->win_full[s]), ph);
                     if (tracer && t == (int)blockIdx.x && kb < 8 && ch == 0) DP_TRACE(8 + kb);
+                    const long long d_0 = (p.trace && tracer) ? clock64() : 0;
                     if (2 * ch + hsel < nhalf) {
                         const uint32_t wbase = win_slot((int)s);
                         const int cbase = kb * 64 + ch * 32;
@@ -348,6 +349,8 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     }
                     // the window slot is free as soon as every lane has consumed its values
                     mbar_arrive(smem_u32(&bars->win_empty[s]));
+                    if (p.trace && tracer && t == (int)blockIdx.x + 2 * (int)gridDim.x && kb == 0 && ch == 0)
+                        p.trace[(size_t)blockIdx.x * 64 + 61] = clock64() - d_0;
                     if (tracer && t == (int)blockIdx.x && kb < 8 && ch == nvalid - 1) DP_TRACE(16 + kb);
                 }
                 if (stored) tmem_st_wait();
@@ -382,6 +385,9 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 const int ncols = (acc_cols - c0) < 32 ? (acc_cols - c0) : 32;   // 32 or 16
                 const uint32_t stg = stg_base + (p.stg_bufs == 2 ? (stg_it & 1u) * 4096u : 0u);
                 uint32_t rr[32];
+                const bool tr = p.trace && ew == 0 && lane == 0 && it == 2 && c0 == esel * 32;   // a steady-state tile
+                long long c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_4 = 0;
+                if (tr) c_0 = clock64();
                 tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&rr[0]));
                 if (ncols == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&rr[16]));
                 else {
@@ -389,6 +395,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     for (int j = 16; j < 32; ++j) rr[j] = 0u;
                 }
                 tmem_ld_wait();
+                if (tr) c_1 = clock64();
                 // folded BN + activation, specialised outside the element loop
 #define K2Y_DP_EPI(ACT_EXPR)                                                                                        \
     _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                                             \
@@ -411,11 +418,13 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     K2Y_DP_EPI(v)
                 }
 #undef K2Y_DP_EPI
+                if (tr) c_2 = clock64();
                 if (lane == 0) {   // the staging buffer about to be overwritten has been read by its store
                     if (p.stg_bufs == 2) tma_store_wait_read1();
                     else tma_store_wait_read0();
                 }
                 __syncwarp();
+                if (tr) c_3 = clock64();
                 // lane = GEMM row i + 8j of the quarter = pixel (x = i, y = j) of the 8x4 block = row of the [y][x][32 ch] store box
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -423,9 +432,18 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                                  rr[j * 4 + 3]);
                 fence_proxy_async();
                 __syncwarp();
+                if (tr) c_4 = clock64();
                 if (lane == 0 && inside) {
                     tma_store_4d(&map_out, stg, c0, px0, py0, b);
                     tma_store_commit();
+                }
+                if (tr) {
+                    long long *o = p.trace + (size_t)blockIdx.x * 64 + 56;
+                    o[0] = c_1 - c_0;
+                    o[1] = c_2 - c_1;
+                    o[2] = c_3 - c_2;
+                    o[3] = c_4 - c_3;
+                    o[4] = clock64() - c_4;
                 }
             }
             tc_fence_before();
@@ -639,6 +657,9 @@ cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights
             for (int kb = 0; kb < p.nkb && kb < 8; ++kb)
                 fprintf(stderr, "[dwpw-trace]   %d: %.2f %.2f %.2f | %.2f %.2f\n", kb, us(8 + kb), us(16 + kb), us(24 + kb), us(32 + kb), us(40 + kb));
             fprintf(stderr, "[dwpw-trace]   epilogue: acc ready %.2f, tile done %.2f, stores drained %.2f, cta end %.2f\n", us(48), us(49), us(50), us(51));
+            fprintf(stderr, "[dwpw-trace]   epilogue chunk cycles (3rd tile): tmem_ld+wait %lld, bn+act %lld, wait_read %lld, sts+fence %lld, tma issue %lld\n",
+                    h[56], h[57], h[58], h[59], h[60]);
+            fprintf(stderr, "[dwpw-trace]   depthwise unit cycles (3rd tile, window landed -> stored): %lld\n", h[61]);
         }
         cudaFree(d_trace);
     }
