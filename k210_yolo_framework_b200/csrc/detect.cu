@@ -504,22 +504,28 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
             tbest = pk[s] > tbest ? pk[s] : tbest;
         }
     }
-    if (tid < 3) s_best[tid] = 0ull;
-    __syncthreads();
-    int nsel = 0, slot = 0;
+    const int warp = tid >> 5;
+    int nsel = 0, par = 0;
     while (nsel < p.maxk) {
+        // per-warp maximum -> s_best[par][warp]; after the barrier every warp reduces the NMS_WARPS entries again (lane w holds
+        // warp w's): two warp-reduce instructions, no shared-memory atomics (a 64-bit atomicMax is a CAS loop that 16
+        // contending warps serialise)
+        unsigned long long wmax = 0ull;
         if (__ballot_sync(FULL, alive != 0u) != 0u) {   // warps whose candidates are all dead only keep the barrier company
             const unsigned hi = (unsigned)(tbest >> 32);
             const unsigned mhi = __reduce_max_sync(FULL, hi);
             const unsigned lo = (alive != 0u && hi == mhi) ? (unsigned)tbest : 0u;
             const unsigned mlo = __reduce_max_sync(FULL, lo);
-            if (lane == 0) atomicMax(&s_best[slot], ((unsigned long long)mhi << 32) | mlo);
+            wmax = ((unsigned long long)mhi << 32) | mlo;
         }
+        if (lane == 0) s_best[par * NMS_WARPS + warp] = wmax;
         __syncthreads();
-        const unsigned long long w = s_best[slot];
-        if (tid == 0) s_best[slot == 0 ? 2 : slot - 1] = 0ull;   // the slot used in the previous round is free again after this barrier...
-        slot = slot == 2 ? 0 : slot + 1;                          // ...and is written next in the round after the next one
-        if (w == 0ull) break;   // nothing alive (a live key is never 0: its score or its index field is non-zero ... or position)
+        const unsigned long long mine = lane < NMS_WARPS ? s_best[par * NMS_WARPS + lane] : 0ull;
+        par ^= 1;
+        const unsigned whi = __reduce_max_sync(FULL, (unsigned)(mine >> 32));
+        const unsigned wlo = __reduce_max_sync(FULL, (unsigned)(mine >> 32) == whi ? (unsigned)mine : 0u);
+        const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
+        if (w == 0ull) break;   // nothing alive (a live key is never 0: its index field is non-zero)
         const int wpos = (int)(w & 0xFFFull);
         const float4 kb = s_box[wpos];
         const float ka = s_area[wpos];
@@ -554,7 +560,7 @@ template <int SLOTS>
 __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasParams p) {
     extern __shared__ __align__(16) unsigned char s_nms[];
     __shared__ int s_red[2][NMS_WARPS][3];
-    __shared__ unsigned long long s_best[3];
+    __shared__ unsigned long long s_best[2 * NMS_WARPS];
     pdl_trigger();
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();

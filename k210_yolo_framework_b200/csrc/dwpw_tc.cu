@@ -36,7 +36,10 @@ namespace {
 
 using namespace ptx;
 
-constexpr int DP_THREADS = 18 * 32;   // warp 0 TMA, warp 1 MMA, warps 2-9 depthwise, warps 10-17 epilogue
+constexpr int DP_THREADS = 18 * 32;   // warps 0-7 depthwise, 8-15 epilogue, 16 MMA issuer, 17 TMA producer
+// (the SM's warp arbiter favours HIGH warp ids: the two single-thread roles everything else waits for get the top ids — with the
+// producer as warp 0 its window loads were issued ~1.3 us late behind the busy epilogue / depthwise warps of its sub-partition)
+constexpr int W_DW0 = 0, W_EPI0 = 8, W_MMA = 16, W_TMA = 17;
 constexpr int WIN_STAGES = 3;
 constexpr int B_STAGES = 2;
 constexpr int MAX_A_STAGES = 4;
@@ -70,7 +73,7 @@ __device__ __forceinline__ long long gtime_ns() {
 }
 #define DP_TRACE(slot)                                                            \
     do {                                                                          \
-        if (p.trace) p.trace[(size_t)blockIdx.x * 64 + (slot)] = gtime_ns();      \
+        if (p.trace) p.trace[(size_t)blockIdx.x * 128 + (slot)] = gtime_ns();      \
     } while (0)
 
 struct __align__(8) DpBarriers {
@@ -153,7 +156,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         prefetch_tmap(&map_blo);
         prefetch_tmap(&map_out);
     }
-    if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_slot), p.tmem_cols);
+    if (warp == W_MMA) tmem_alloc(smem_u32(&bars->tmem_slot), p.tmem_cols);
     {
         float *ss = reinterpret_cast<float *>(smem_gen + p.off_ss);   // [n_pass*BN] scale, then shift
         const int ncol = p.n_pass * p.BN;
@@ -175,7 +178,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     auto b_slot = [&](int s) { return smem_base + p.off_b + (uint32_t)s * 2u * b_plane; };
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // ================= TMA producer =================
         uint32_t wseq = 0, bseq = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -193,6 +196,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                         mbar_arrive_expect_tx(fb, p.win_tx);
                         tma_load_4d(win_slot((int)s), &map_in, fb, c0, x0 - 1, y0 - 1, b);
                         if (t == (int)blockIdx.x && wseq < 6) DP_TRACE(2 + wseq);
+                        if (p.trace && kb == 0 && ch == 0 && (t - (int)blockIdx.x) / (int)gridDim.x < 10) DP_TRACE(64 + 6 * ((t - (int)blockIdx.x) / (int)gridDim.x) + 5);
                     }
                     __syncwarp();
                     ++wseq;
@@ -211,7 +215,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_bf16(128, p.BN);
         uint32_t kc = 0, bseq = 0, it = 0;
@@ -245,26 +249,29 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                         if (np == p.n_pass - 1) {
                             if (t == (int)blockIdx.x && kb < 8) DP_TRACE(40 + kb);
                             umma_commit(smem_u32(&bars->a_empty[as]));
-                            if (kb == p.nkb - 1) umma_commit(smem_u32(&bars->tmem_full[a]));
+                            if (kb == p.nkb - 1) {
+                                umma_commit(smem_u32(&bars->tmem_full[a]));
+                                if (p.trace && it < 10) DP_TRACE(64 + 6 * it + 2);
+                            }
                         }
                     }
                     __syncwarp();
                 }
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < W_EPI0) {
         // ================= depthwise: shared-memory window -> registers -> (hi, mid) bf16 planes in tensor memory =================
         // Work unit = (8x4 block q, 16-channel half h of the k-block): thread (i = lane/4, m = lane%4) computes the 4 vertically
         // adjacent pixels (x = i, y = 0..3) of ONE channel quad.  Under the weight k-permutation (gemm_tc.h d_bh_p) the tensor
         // memory columns 8u + 2m (+1) of a 32-channel chunk hold channels 8m + 4u .. +3, i.e. thread m of half u reads quad
         // 2m + u: the 8 lanes of a quarter warp touch all eight 16-byte chunks of their pixels' 128-byte lines (no bank conflict).
         const int q = warp & 3;            // TMEM lane quarter this warp may touch == the 8x4 block of the tile it computes
-        const int hsel = (warp - 2) >> 2;  // this warp takes halves hsel and hsel + 2 of every k-block (= unit hsel of chunk 0 / 1)
+        const int hsel = (warp - W_DW0) >> 2;  // this warp takes halves hsel and hsel + 2 of every k-block (= unit hsel of chunk 0 / 1)
         const int bx = q % p.tw, by = q / p.tw;
         const int i = lane >> 2, m = lane & 3;
         const int quad = 2 * m + hsel;     // channel quad inside a 32-channel chunk
         const int WC = p.win_cols;
-        const bool tracer = warp == 2 && lane == 0;
+        const bool tracer = warp == W_DW0 + 2 && lane == 0;
         mbar_wait(smem_u32(&bars->par_full), 0u);
         float4 w9[9];
         auto load_taps = [&](int cbase) {
@@ -288,9 +295,10 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     const uint32_t s = seq % WIN_STAGES, ph = (seq / WIN_STAGES) & 1u;
                     mbar_wait(smem_u32(&bars->win_full[s]), ph);
                     if (tracer && t == (int)blockIdx.x && kb < 8 && ch == 0) DP_TRACE(8 + kb);
+                    if (p.trace && tracer && kb == 0 && ch == 0 && (t - (int)blockIdx.x) / (int)gridDim.x < 10) DP_TRACE(64 + 6 * ((t - (int)blockIdx.x) / (int)gridDim.x));
                     const long long d_0 = (p.trace && tracer) ? clock64() : 0;
                     if (2 * ch + hsel < nhalf) {
-                        const uint32_t wbase = win_slot((int)s);
+                        const uint8_t *wptr = smem_gen + (size_t)s * p.win_bytes;   // plain loads: the compiler may batch them
                         const int cbase = kb * 64 + ch * 32;
                         if (!hoist) load_taps(cbase);
                         float4 acc[4];
@@ -302,7 +310,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
                                 const uint32_t pix = (uint32_t)((by * 4 + wy) * WC + bx * 8 + i + dx);
-                                v[dx] = ld_shared_v4(wbase + pix * 128u + ((((uint32_t)quad) ^ (pix & 7u)) << 4));
+                                v[dx] = *reinterpret_cast<const float4 *>(wptr + pix * 128u + ((((uint32_t)quad) ^ (pix & 7u)) << 4));
                             }
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy) {
@@ -350,11 +358,12 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     // the window slot is free as soon as every lane has consumed its values
                     mbar_arrive(smem_u32(&bars->win_empty[s]));
                     if (p.trace && tracer && t == (int)blockIdx.x + 2 * (int)gridDim.x && kb == 0 && ch == 0)
-                        p.trace[(size_t)blockIdx.x * 64 + 61] = clock64() - d_0;
+                        p.trace[(size_t)blockIdx.x * 128 + 61] = clock64() - d_0;
                     if (tracer && t == (int)blockIdx.x && kb < 8 && ch == nvalid - 1) DP_TRACE(16 + kb);
                 }
                 if (stored) tmem_st_wait();
                 if (tracer && t == (int)blockIdx.x && kb < 8) DP_TRACE(24 + kb);
+                if (p.trace && tracer && kb == p.nkb - 1 && (t - (int)blockIdx.x) / (int)gridDim.x < 10) DP_TRACE(64 + 6 * ((t - (int)blockIdx.x) / (int)gridDim.x) + 1);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars->a_full[as]));
                 wseq += (uint32_t)nvalid;
@@ -362,13 +371,12 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         }
     } else {
         // ================= epilogue: two warps per TMEM quarter, alternating 32-column chunks =================
-        const int ew = warp - 10;
+        const int ew = warp - W_EPI0;
         const int q = warp & 3;
         const int esel = ew >> 2;
         const int bx = q % p.tw, by = q / p.tw;
         const uint32_t stg_base = smem_base + p.off_stage + (uint32_t)ew * 4096u * (uint32_t)p.stg_bufs;
-        const uint32_t ss = smem_base + p.off_ss;
-        const uint32_t sh_off = (uint32_t)acc_cols * 4u;
+        const float *ssp = reinterpret_cast<const float *>(smem_gen + p.off_ss);   // [acc_cols] scale, [acc_cols] shift
         const int n_lim = (p.N + 15) & ~15;
         uint32_t it = 0, stg_it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -380,6 +388,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             mbar_wait(smem_u32(&bars->tmem_full[a]), aph);
             tc_fence_after();
             if (ew == 0 && lane == 0 && t == (int)blockIdx.x) DP_TRACE(48);
+            if (p.trace && ew == 0 && lane == 0 && it < 10) DP_TRACE(64 + 6 * it + 3);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)acc_cols;
             for (int c0 = esel * 32; c0 < acc_cols && c0 < n_lim; c0 += 64, ++stg_it) {
                 const int ncols = (acc_cols - c0) < 32 ? (acc_cols - c0) : 32;   // 32 or 16
@@ -399,8 +408,8 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 // folded BN + activation, specialised outside the element loop
 #define K2Y_DP_EPI(ACT_EXPR)                                                                                        \
     _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                                             \
-        const float4 s4 = ld_shared_v4(ss + (uint32_t)(c0 + j) * 4u);                                               \
-        const float4 h4 = ld_shared_v4(ss + sh_off + (uint32_t)(c0 + j) * 4u);                                      \
+        const float4 s4 = *reinterpret_cast<const float4 *>(ssp + c0 + j);                                          \
+        const float4 h4 = *reinterpret_cast<const float4 *>(ssp + acc_cols + c0 + j);                               \
         float v;                                                                                                     \
         v = fmaf(__uint_as_float(rr[j]), s4.x, h4.x);     rr[j] = __float_as_uint(ACT_EXPR);                         \
         v = fmaf(__uint_as_float(rr[j + 1]), s4.y, h4.y); rr[j + 1] = __float_as_uint(ACT_EXPR);                     \
@@ -438,7 +447,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                     tma_store_commit();
                 }
                 if (tr) {
-                    long long *o = p.trace + (size_t)blockIdx.x * 64 + 56;
+                    long long *o = p.trace + (size_t)blockIdx.x * 128 + 56;
                     o[0] = c_1 - c_0;
                     o[1] = c_2 - c_1;
                     o[2] = c_3 - c_2;
@@ -449,6 +458,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->tmem_empty[a]));
             if (ew == 0 && lane == 0 && t == (int)blockIdx.x) DP_TRACE(49);
+            if (p.trace && ew == 0 && lane == 0 && it < 10) DP_TRACE(64 + 6 * it + 4);
         }
         if (lane == 0) tma_store_wait_all();
         if (ew == 0 && lane == 0) DP_TRACE(50);
@@ -457,7 +467,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) DP_TRACE(51);
-    if (warp == 1) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
@@ -636,8 +646,8 @@ cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights
     const char *tr = getenv("K2Y_TC_TRACE");
     long long *d_trace = nullptr;
     if (tr && tr[0] == '1') {
-        cudaMalloc(&d_trace, (size_t)plan.grid * 64 * sizeof(long long));
-        cudaMemset(d_trace, 0, (size_t)plan.grid * 64 * sizeof(long long));
+        cudaMalloc(&d_trace, (size_t)plan.grid * 128 * sizeof(long long));
+        cudaMemset(d_trace, 0, (size_t)plan.grid * 128 * sizeof(long long));
         p.trace = d_trace;
         cfg.numAttrs = 0;
     }
@@ -645,11 +655,11 @@ cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights
     if (e != cudaSuccess) return e;
     if (d_trace) {
         cudaStreamSynchronize(st);
-        long long h[64];
+        long long h[128];
         fprintf(stderr, "[dwpw-trace] %dx%d C=%d N=%d tile %dx%d tiles=%d grid=%d nkb=%d BN=%d n_pass=%d acc_stages=%d a_stages=%d smem=%zu\n", p.H, p.W,
                 p.C, p.N, 8 * p.tw, 4 * p.th, p.num_tiles, plan.grid, p.nkb, p.BN, p.n_pass, p.acc_stages, p.a_stages, plan.smem);
         for (int cta : {0, plan.grid - 1}) {
-            cudaMemcpy(h, d_trace + (size_t)cta * 64, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaMemcpy(h, d_trace + (size_t)cta * 128, sizeof(h), cudaMemcpyDeviceToHost);
             auto us = [&](int i) { return h[i] ? (h[i] - h[0]) * 1e-3 : -1.0; };
             fprintf(stderr, "[dwpw-trace] cta %d: setup %.2f | win issue", cta, us(1));
             for (int i = 0; i < 6; ++i) fprintf(stderr, " %.2f", us(2 + i));
@@ -660,6 +670,10 @@ cudaError_t launch_dwpw_tc(const DwArgs &dw, const ConvArgs &pw, const TcWeights
             fprintf(stderr, "[dwpw-trace]   epilogue chunk cycles (3rd tile): tmem_ld+wait %lld, bn+act %lld, wait_read %lld, sts+fence %lld, tma issue %lld\n",
                     h[56], h[57], h[58], h[59], h[60]);
             fprintf(stderr, "[dwpw-trace]   depthwise unit cycles (3rd tile, window landed -> stored): %lld\n", h[61]);
+            fprintf(stderr, "[dwpw-trace]   tile: win_issued dw_start dw_done mma_issued epi_start epi_done\n");
+            for (int ti = 0; ti < 10; ++ti)
+                fprintf(stderr, "[dwpw-trace]   %d: %.2f %.2f %.2f %.2f %.2f %.2f\n", ti, us(64 + 6 * ti + 5), us(64 + 6 * ti), us(64 + 6 * ti + 1), us(64 + 6 * ti + 2),
+                        us(64 + 6 * ti + 3), us(64 + 6 * ti + 4));
         }
         cudaFree(d_trace);
     }

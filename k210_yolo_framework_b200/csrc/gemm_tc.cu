@@ -166,7 +166,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     Barriers *bars = reinterpret_cast<Barriers *>(smem_gen + (size_t)p.stages * stage_bytes);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Role ids run AGAINST the hardware warp ids: the SM's warp arbiter favours high warp ids, and the two single-thread roles
+    // everything else waits for (role 0 = TMA producer, role 1 = MMA issuer) must not queue behind busy epilogue / converter
+    // warps of their sub-partition.  `warp` below is the role id (0 producer, 1 MMA, 2-5 gather, 6-9 converter, 10-13
+    // epilogue), `pq` the tensor-memory lane quarter the hardware lets this warp touch (physical warp id % 4).
+    const int phys_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (NUM_THREADS / 32 - 1) - phys_warp;
+    const int pq = phys_warp & 3;
     pdl_trigger();
     const bool use_conv = p.three_x || GATHER;
     const int crank = p.cluster == 2 ? (int)cluster_ctarank() : 0;
@@ -214,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // TMEM -> registers (lane = GEMM row) -> BN-fold/activation -> 128B-swizzled smem staging [32 rows][32 cols]
         // per warp -> either one TMA store per 32-column chunk (full-line writes, no LSU work) or, for N % 4 != 0 /
         // residual layers, row-contiguous st.global (a warp instruction covers 4 rows x 128 contiguous bytes).
-        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int q = pq;                       // TMEM lane quarter this warp may read
         const bool n_vec = (p.N & 3) == 0;
         // two 4 KB staging buffers per warp, 1024-byte aligned (SWIZZLE_128B atom)
         // staging: 32 KB after the barriers.  One epilogue group: 2 x 4 KB per warp (double buffered against its TMA store);
@@ -489,7 +495,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // ---- fused depthwise producer: the A tile is computed, not copied (one k-block per tile, K = C0 <= 64) ----
             // work item = (channel quad, 4 consecutive GEMM rows = 4 horizontally adjacent output pixels; OW % 4 == 0);
             // lanes run over the channel quads first, so a load instruction reads whole pixels' channel runs.
-            const int g = threadIdx.x - 64;
+            const int g = (warp - 2) * 32 + lane;
             const int c4n = p.C0 >> 2;
             for (int s2 = 0; s2 < p.stages; ++s2)  // columns >= C0 stay zero for the whole kernel (weights there are zero too)
                 for (uint32_t i = (uint32_t)g; i < a_bytes / 16u; i += 128u) st_shared_v4(stage_a_hi(s2) + i * 16u, 0u, 0u, 0u, 0u);
@@ -536,7 +542,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         } else if (GATHER) {
-            const int r = threadIdx.x - 64;  // GEMM row inside the tile, 0..127
+            const int r = (warp - 2) * 32 + lane;  // GEMM row inside the tile, 0..127
             const int Cin = p.C0 + p.C1;
             const int wrow0 = (warp - 2) * 32;   // first tile row of this warp
             int s = 0;
@@ -611,7 +617,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp >= 6 && warp < 10) {
         // ================= converter: fp32 -> (hi, lo) tf32 planes =================
         if (use_conv) {
-            const int ct = threadIdx.x - 6 * 32;  // 0..127
+            const int ct = (warp - 6) * 32 + lane;  // 0..127
             int s = 0;
             uint32_t ph = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -622,7 +628,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (t == cluster_id && kb - kb0 < 8 && ct == 0) K2Y_TRACE(16 + (kb - kb0) * 4 + 1);
                     if (p.bf16) {
                         // thread = GEMM row: 64 fp32 -> bf16 hi plane (32 columns) + bf16 mid plane (32 columns) in TMEM
-                        const int row = (warp & 3) * 32 + lane;
+                        const int row = pq * 32 + lane;
                         uint32_t hi[32], lo[32];
 #pragma unroll
                         for (int bx = 0; bx < 2; ++bx) {
@@ -639,14 +645,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 lo[bx * 16 + j * 2 + 1] = pack_bf16x2(r2, r3);
                             }
                         }
-                        const uint32_t trow = tmem_a_hi(s) + ((uint32_t)((warp & 3) * 32) << 16);
+                        const uint32_t trow = tmem_a_hi(s) + ((uint32_t)(pq * 32) << 16);
                         tmem_st32(trow, hi);
                         tmem_st32(trow + 32u, lo);
                         tmem_st_wait();
                         tc_fence_before();
                     } else if (p.three_x) {
                         // thread = GEMM row: read its 128-byte (swizzled) k-slice, split, write both planes to TMEM
-                        const int row = (warp & 3) * 32 + lane;
+                        const int row = pq * 32 + lane;
                         const uint32_t src = stage_a_hi(s) + (uint32_t)row * 128u;
                         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -662,7 +668,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             lo[j * 4 + 2] = __float_as_uint(to_tf32_rna(v.z - h2));
                             lo[j * 4 + 3] = __float_as_uint(to_tf32_rna(v.w - h3));
                         }
-                        const uint32_t trow = tmem_a_hi(s) + ((uint32_t)((warp & 3) * 32) << 16);
+                        const uint32_t trow = tmem_a_hi(s) + ((uint32_t)(pq * 32) << 16);
                         tmem_st32(trow, hi);
                         tmem_st32(trow + 32u, lo);
                         tmem_st_wait();
