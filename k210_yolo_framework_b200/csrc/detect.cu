@@ -174,7 +174,7 @@ struct KerasParams {
     unsigned long long *keys;         // [B][C][P] candidate sort keys
     int *ncand;                       // [B][C] candidates per (image, class); zeroed before the scan
     unsigned *alive;                  // [B][C][P/32] (only used when a class has more candidates than fit shared memory)
-    int cap;                          // candidates the NMS kernel can hold in shared memory (keys 8 B + box 16 B + area 4 B each)
+    int cap;                          // candidates the NMS kernel can hold in shared memory (key 8 B + decoded box 16 B each)
 };
 
 // Collects the candidates of one class (score passes `pred`) in index order, sorts them.
@@ -481,7 +481,7 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
 // warp -> barrier -> everybody reads the winner and its box -> IoU tests of the own (register) candidates, unrolled.
 template <int SLOTS>
 __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, const unsigned long long *s_keys, const float4 *s_box,
-                                               const float *s_area, const float4 *gboxes, k2y_det *out, unsigned long long *s_best) {
+                                               k2y_det *out, unsigned long long *s_best) {
     const int tid = threadIdx.x, lane = tid & 31;
     unsigned long long pk[SLOTS];
     float4 bx[SLOTS];
@@ -498,8 +498,7 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
             const unsigned long long k = s_keys[pos];
             // (score, ~index) -> (score, 20-bit ~index, 12-bit position); + 1 in the position field keeps the key non-zero
             pk[s] = (k & 0xffffffff00000000ull) | ((unsigned long long)(0xFFFFFu - (unsigned)key_index(k)) << 12) | (unsigned long long)pos;
-            bx[s] = s_box[pos];
-            ar[s] = s_area[pos];
+            bx[s] = norm_box(s_box[pos], ar[s]);
             alive |= 1u << s;
             tbest = pk[s] > tbest ? pk[s] : tbest;
         }
@@ -527,12 +526,12 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
         const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
         if (w == 0ull) break;   // nothing alive (a live key is never 0: its index field is non-zero)
         const int wpos = (int)(w & 0xFFFull);
-        const float4 kb = s_box[wpos];
-        const float ka = s_area[wpos];
+        const float4 ob = s_box[wpos];       // as decoded (the record keeps these); every thread normalises its own copy
+        float ka;
+        const float4 kb = norm_box(ob, ka);
         if (tid == 0) {
             const int index = (int)(0xFFFFFu - (unsigned)((w >> 12) & 0xFFFFFull));
             k2y_det d;
-            const float4 ob = gboxes[index];
             d.ymin = ob.x;
             d.xmin = ob.y;
             d.ymax = ob.z;
@@ -607,19 +606,16 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
 
     int nsel;
     if (n <= p.cap) {
-        // keys, (min,max)-normalised boxes and areas of all candidates in shared memory (arrival order: no sort needed)
+        // keys and decoded boxes of all candidates in shared memory (arrival order: no sort needed)
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_nms);
         float4 *s_box = reinterpret_cast<float4 *>(s_nms + (size_t)p.cap * 8);
-        float *s_area = reinterpret_cast<float *>(s_nms + (size_t)p.cap * 24);
         for (int i = tid; i < n; i += NMS_THREADS) {
             const unsigned long long k = gkeys[i];
             s_keys[i] = k;
-            float ar;
-            s_box[i] = norm_box(gboxes[key_index(k)], ar);
-            s_area[i] = ar;
+            s_box[i] = gboxes[key_index(k)];
         }
         __syncthreads();
-        nsel = nms_rounds_smem<SLOTS>(p, n, s_keys, s_box, s_area, gboxes, out, s_best);
+        nsel = nms_rounds_smem<SLOTS>(p, n, s_keys, s_box, out, s_best);
     } else {
         unsigned *alive_g = p.alive + ((size_t)b * p.C + c) * (size_t)(p.P >> 5);
         nsel = nms_rounds<false>(p, n, gkeys, nullptr, nullptr, gboxes, alive_g, out, s_red);
@@ -827,7 +823,7 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 using namespace k2y;
 
 namespace {
-constexpr int NMS_SMEM_CAP = 4096;  // candidates of one class held in shared memory (28 bytes each); more -> global-memory path
+constexpr int NMS_SMEM_CAP = 4096;  // candidates of one class held in shared memory (24 bytes each); more -> global-memory path
 
 struct DetectLayout {
     size_t nbox, P, boxes_off, keys_off, ncand_off, alive_off, total;
@@ -939,7 +935,7 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     p.cap = L.cap;
     const size_t scan_smem = (size_t)SCAN_BOXES * (5 + p.C + 2) * sizeof(float);
     p.c_magic = (unsigned)((0x100000000ull + (unsigned long long)p.C - 1ull) / (unsigned long long)p.C);
-    const size_t nms_smem = (size_t)p.cap * 28;  // keys + boxes + areas
+    const size_t nms_smem = (size_t)p.cap * 24;  // keys + decoded boxes
     int dev = 0;
     K2Y_CUDA_CHECK(cudaGetDevice(&dev));
     static bool attr_set[64] = {false};  // per device: opt-in shared memory is a per-device function attribute
