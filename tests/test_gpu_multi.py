@@ -34,15 +34,22 @@ for rep in range(3):                                  # three steps: both gather
     xs = np.roll(x_all, rep, axis=0)
     d, c = pipe.detect_host(torch.from_numpy(xs[rank * B:(rank + 1) * B].copy()).pin_memory())
     outs.append(DetectionPipeline.records(d.clone(), c.clone()))
-ok = True
+ok, why = True, ""
 if rank == 0:
-    single = make(1, 0, world * B)
+    # reference: ONE GPU, the same per-rank batch size (same tile plans, same accumulation order -> same bits), shard by shard
+    single = make(1, 0, B)
     for rep in range(3):
         xs = np.roll(x_all, rep, axis=0)
-        d, c = single.detect_host(torch.from_numpy(xs.copy()).pin_memory())
-        ref = DetectionPipeline.records(d.clone(), c.clone())
-        ok &= (ref == outs[rep]) and sum(len(i) for i in ref) > 50
-    print("K2Y_MULTI " + json.dumps({"ok": bool(ok), "world": world, "nccl": pipe.gather.comm.nccl_version()}), flush=True)
+        ref = []
+        for r in range(world):
+            d, c = single.detect_host(torch.from_numpy(xs[r * B:(r + 1) * B].copy()).pin_memory())
+            ref += DetectionPipeline.records(d.clone(), c.clone())
+        if ref != outs[rep]:
+            bad = [i for i, (a, b) in enumerate(zip(ref, outs[rep])) if a != b]
+            why += f" rep {rep}: images {bad} differ ({[len(ref[i]) for i in bad]} vs {[len(outs[rep][i]) for i in bad]} records);"
+            ok = False
+        ok &= sum(len(i) for i in ref) > 50
+    print("K2Y_MULTI " + json.dumps({"ok": bool(ok), "world": world, "nccl": pipe.gather.comm.nccl_version(), "why": why}), flush=True)
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -63,4 +70,4 @@ def test_gathered_records_equal_single_gpu(tmp_path):
     line = [l for l in r.stdout.splitlines() if l.startswith("K2Y_MULTI ")]
     assert line, r.stdout[-2000:]
     res = json.loads(line[0][len("K2Y_MULTI "):])
-    assert res["ok"] and res["world"] == world
+    assert res["ok"] and res["world"] == world, res
