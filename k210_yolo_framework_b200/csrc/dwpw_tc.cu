@@ -130,19 +130,19 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         DP_TRACE(0);
         for (int s = 0; s < WIN_STAGES; ++s) {
             mbar_init(smem_u32(&bars->win_full[s]), 1);
-            mbar_init(smem_u32(&bars->win_empty[s]), 256);
+            mbar_init(smem_u32(&bars->win_empty[s]), 8);    // one arrival per depthwise warp
         }
         for (int s = 0; s < B_STAGES; ++s) {
             mbar_init(smem_u32(&bars->b_full[s]), 1);
             mbar_init(smem_u32(&bars->b_empty[s]), 1);
         }
         for (int s = 0; s < MAX_A_STAGES; ++s) {
-            mbar_init(smem_u32(&bars->a_full[s]), 256);
+            mbar_init(smem_u32(&bars->a_full[s]), 8);
             mbar_init(smem_u32(&bars->a_empty[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&bars->tmem_full[a]), 1);
-            mbar_init(smem_u32(&bars->tmem_empty[a]), 256);
+            mbar_init(smem_u32(&bars->tmem_empty[a]), 8);  // one arrival per epilogue warp
         }
         mbar_init(smem_u32(&bars->par_full), 1);
         fence_barrier_init();
@@ -355,8 +355,10 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                         }
                         stored = true;
                     }
-                    // the window slot is free as soon as every lane has consumed its values
-                    mbar_arrive(smem_u32(&bars->win_empty[s]));
+                    // the window slot is free as soon as every lane has consumed its values; ONE arrival per warp (256 per-thread
+                    // arrivals on one mbarrier serialise in the shared-memory atomic unit)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->win_empty[s]));
                     if (p.trace && tracer && t == (int)blockIdx.x + 2 * (int)gridDim.x && kb == 0 && ch == 0)
                         p.trace[(size_t)blockIdx.x * 128 + 61] = clock64() - d_0;
                     if (tracer && t == (int)blockIdx.x && kb < 8 && ch == nvalid - 1) DP_TRACE(16 + kb);
@@ -365,7 +367,8 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 if (tracer && t == (int)blockIdx.x && kb < 8) DP_TRACE(24 + kb);
                 if (p.trace && tracer && kb == p.nkb - 1 && (t - (int)blockIdx.x) / (int)gridDim.x < 10) DP_TRACE(64 + 6 * ((t - (int)blockIdx.x) / (int)gridDim.x) + 1);
                 tc_fence_before();
-                mbar_arrive(smem_u32(&bars->a_full[as]));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[as]));
                 wseq += (uint32_t)nvalid;
             }
         }
@@ -456,7 +459,8 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 }
             }
             tc_fence_before();
-            mbar_arrive(smem_u32(&bars->tmem_empty[a]));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[a]));
             if (ew == 0 && lane == 0 && t == (int)blockIdx.x) DP_TRACE(49);
             if (p.trace && ew == 0 && lane == 0 && it < 10) DP_TRACE(64 + 6 * it + 4);
         }

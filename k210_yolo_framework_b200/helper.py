@@ -72,7 +72,7 @@ class Helper(object):
         (``predict_device_u8``), which applies ``img / np.max(img)`` on the GPU."""
         import torch
         from .preprocess import letterbox_device
-        x = torch.from_numpy(np.ascontiguousarray(img[..., :3], dtype=np.uint8)).cuda()
+        x = torch.from_numpy(np.array(img[..., :3], dtype=np.uint8, order="C", copy=True)).cuda()
         return letterbox_device(x, self.in_hw[0])
 
 
