@@ -173,7 +173,8 @@ struct KerasParams {
     float4 *boxes;                    // [B][nbox] decoded (ymin,xmin,ymax,xmax) of every box
     unsigned long long *keys;         // [B][C][P] candidate sort keys
     int *ncand;                       // [B][C] candidates per (image, class); zeroed before the scan
-    unsigned *alive;                  // [B][C][P/32] (only used when a class has more candidates than fit shared memory)
+    unsigned *alive;                  // [B][C][alive_stride] liveness words (only when a class has more candidates than fit shared memory)
+    int alive_stride;
     int cap;                          // candidates the NMS kernel can hold in shared memory (key 8 B + decoded box 16 B each)
 };
 
@@ -354,8 +355,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
 // warp-reduce instructions on the (score bits, ~index, position) triple + one shared-memory exchange) followed by one
 // IoU test per live candidate, all candidates spread over the CTA's threads.  The selection order is exactly the order of
 // the sorted keys (score descending, index ascending), so the records equal the sequential algorithm's.
-constexpr int NMS_THREADS = 512;
-constexpr int NMS_WARPS = NMS_THREADS / 32;
+constexpr int NMS_MAX_WARPS = 16;   // the kernel runs with 256 (cap <= 2048) or 512 threads
 
 __device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long long key, const float4 kb) {
     k2y_det d;
@@ -368,9 +368,10 @@ __device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long 
     out[slot] = d;
 }
 
-template <bool SMEM>
+template <bool SMEM, int NMS_THREADS>
 __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const unsigned long long *keys, const float4 *s_box, const float *s_area,
-                                          const float4 *gboxes, unsigned *alive_g, k2y_det *out, int (*s_red)[NMS_WARPS][3]) {
+                                          const float4 *gboxes, unsigned *alive_g, k2y_det *out, int (*s_red)[NMS_MAX_WARPS][3]) {
+    constexpr int NMS_WARPS = NMS_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // candidate `pos` belongs to thread pos % NMS_THREADS; its liveness is bit (pos / NMS_THREADS) % 32 of the thread's mask word
     // (pos / NMS_THREADS) / 32 — one register in the shared-memory path (cap <= 32 * NMS_THREADS), global words otherwise
@@ -479,9 +480,10 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
 // 12 bits never decide a comparison (the (score, index) pair is unique), so ONE 64-bit maximum yields the winner and where its
 // box sits in shared memory.  A round: per-warp maximum (two warp-reduce instructions) -> one shared-memory atomicMax per
 // warp -> barrier -> everybody reads the winner and its box -> IoU tests of the own (register) candidates, unrolled.
-template <int SLOTS>
+template <int NMS_THREADS, int SLOTS>
 __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, const unsigned long long *s_keys, const float4 *s_box,
                                                k2y_det *out, unsigned long long *s_best) {
+    constexpr int NMS_WARPS = NMS_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31;
     unsigned long long pk[SLOTS];
     float4 bx[SLOTS];
@@ -553,13 +555,16 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
     return nsel;
 }
 
-// SLOTS = candidates per thread of the shared-memory path (cap / NMS_THREADS rounded up to 2, 4 or 8): one kernel per value so
-// that the small grids (1050 boxes -> 3 candidates per thread) are not compiled at the register count of the largest
-template <int SLOTS>
+// NMS_THREADS x SLOTS >= cap candidates of the shared-memory path: 256 threads for the common grids (every warp pays a fixed
+// per-round cost — reduce, barrier, winner look-up — whether or not it still has live candidates, so fewer, fuller warps win:
+// 28 -> ... us on the cfg-2 bench workload), 512 only for cap > 2048.  One kernel per pair so that the small grids are not
+// compiled at the register count of the largest.
+template <int NMS_THREADS, int SLOTS>
 __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasParams p) {
+    constexpr int NMS_WARPS = NMS_THREADS / 32;
     extern __shared__ __align__(16) unsigned char s_nms[];
-    __shared__ int s_red[2][NMS_WARPS][3];
-    __shared__ unsigned long long s_best[2 * NMS_WARPS];
+    __shared__ int s_red[2][NMS_MAX_WARPS][3];
+    __shared__ unsigned long long s_best[2 * NMS_MAX_WARPS];
     pdl_trigger();
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
@@ -615,10 +620,10 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
             s_box[i] = gboxes[key_index(k)];
         }
         __syncthreads();
-        nsel = nms_rounds_smem<SLOTS>(p, n, s_keys, s_box, out, s_best);
+        nsel = nms_rounds_smem<NMS_THREADS, SLOTS>(p, n, s_keys, s_box, out, s_best);
     } else {
-        unsigned *alive_g = p.alive + ((size_t)b * p.C + c) * (size_t)(p.P >> 5);
-        nsel = nms_rounds<false>(p, n, gkeys, nullptr, nullptr, gboxes, alive_g, out, s_red);
+        unsigned *alive_g = p.alive + ((size_t)b * p.C + c) * (size_t)p.alive_stride;
+        nsel = nms_rounds<false, NMS_THREADS>(p, n, gkeys, nullptr, nullptr, gboxes, alive_g, out, s_red);
     }
     if (tid == 0) *count_out = nsel;
 }
@@ -826,7 +831,7 @@ namespace {
 constexpr int NMS_SMEM_CAP = 4096;  // candidates of one class held in shared memory (24 bytes each); more -> global-memory path
 
 struct DetectLayout {
-    size_t nbox, P, boxes_off, keys_off, ncand_off, alive_off, total;
+    size_t nbox, P, boxes_off, keys_off, ncand_off, alive_off, alive_stride, total;
     int cap;
 };
 // workspace: [boxes B*nbox float4][keys B*C*P u64][ncand B*C int][alive B*C*P/32 u32]
@@ -835,7 +840,7 @@ DetectLayout detect_layout(const k2y_detect_cfg *cfg, int batch) {
     L.nbox = 0;
     for (int l = 0; l < cfg->n_layers; ++l) L.nbox += (size_t)cfg->layer_h[l] * cfg->layer_w[l] * cfg->anchor_num;
     L.P = (size_t)next_pow2((int)L.nbox);
-    L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 511) / 512 * 512) : (size_t)NMS_SMEM_CAP);
+    L.cap = (int)(L.nbox < (size_t)NMS_SMEM_CAP ? ((L.nbox + 255) / 256 * 256) : (size_t)NMS_SMEM_CAP);
     if (L.nbox >= 0xFFFFFu) L.cap = 0;  // the shared-memory path packs the box index into 20 bits of its sort key
     const size_t BC = (size_t)batch * cfg->class_num;
     size_t off = 256;  // alignment slack
@@ -846,7 +851,8 @@ DetectLayout detect_layout(const k2y_detect_cfg *cfg, int batch) {
     L.ncand_off = off;
     off += align256(BC * sizeof(int));
     L.alive_off = off;
-    off += L.nbox > (size_t)L.cap ? align256(BC * (L.P / 32) * sizeof(unsigned)) : 0;
+    L.alive_stride = (L.P / 32 + 511) / 512 * 512 + 512;   // whole words per thread, 512 threads at most
+    off += L.nbox > (size_t)L.cap ? align256(BC * L.alive_stride * sizeof(unsigned)) : 0;
     L.total = off;
     return L;
 }
@@ -933,6 +939,7 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     p.ncand = reinterpret_cast<int *>(ws + L.ncand_off);
     p.alive = reinterpret_cast<unsigned *>(ws + L.alive_off);
     p.cap = L.cap;
+    p.alive_stride = (int)L.alive_stride;
     const size_t scan_smem = (size_t)SCAN_BOXES * (5 + p.C + 2) * sizeof(float);
     p.c_magic = (unsigned)((0x100000000ull + (unsigned long long)p.C - 1ull) / (unsigned long long)p.C);
     const size_t nms_smem = (size_t)p.cap * 24;  // keys + decoded boxes
@@ -940,9 +947,9 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     K2Y_CUDA_CHECK(cudaGetDevice(&dev));
     static bool attr_set[64] = {false};  // per device: opt-in shared memory is a per-device function attribute
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
-        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
-        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 28));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 24));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 24));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 24));
         K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set[dev] = true;
     }
@@ -955,9 +962,9 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     dim3 sgrid((p.nbox + SCAN_BOXES - 1) / SCAN_BOXES, batch);
     detect_scan_kernel<<<sgrid, SCAN_THREADS, scan_smem, st>>>(p);  // follows a memset: plain stream order
     K2Y_CUDA_CHECK(cudaGetLastError());
-    if (p.cap <= 2 * NMS_THREADS) launch_k(detect_nms_kernel<2>, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
-    else if (p.cap <= 4 * NMS_THREADS) launch_k(detect_nms_kernel<4>, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
-    else launch_k(detect_nms_kernel<8>, dim3(p.C, batch), dim3(NMS_THREADS), nms_smem, st, p);
+    if (p.cap <= 1024) launch_k(detect_nms_kernel<256, 4>, dim3(p.C, batch), dim3(256), nms_smem, st, p);
+    else if (p.cap <= 2048) launch_k(detect_nms_kernel<256, 8>, dim3(p.C, batch), dim3(256), nms_smem, st, p);
+    else launch_k(detect_nms_kernel<512, 8>, dim3(p.C, batch), dim3(512), nms_smem, st, p);
     K2Y_CUDA_CHECK(cudaGetLastError());
     return K2Y_OK;
 }
