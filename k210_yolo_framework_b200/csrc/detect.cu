@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
 // IoU test per live candidate, all candidates spread over the CTA's threads.  The selection order is exactly the order of
 // the sorted keys (score descending, index ascending), so the records equal the sequential algorithm's.
 constexpr int NMS_MAX_WARPS = 16;   // the kernel runs with 256 (cap <= 2048) or 512 threads
+constexpr int WARP_SLOTS = 8;       // candidates per lane of the single-warp path (<= 256 candidates)
 
 __device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long long key, const float4 kb) {
     k2y_det d;
@@ -578,30 +579,62 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
     const unsigned long long *gkeys = p.keys + ((size_t)b * p.C + c) * p.P;
     const float4 *gboxes = p.boxes + (size_t)b * p.nbox;
 
-    if (n <= 32) {
-        // ---- a handful of candidates (every real image): one warp, keys and boxes in registers ----
+    if (n <= 32 * WARP_SLOTS && n <= p.cap && p.nbox < 0xFFFFF) {
+        // ---- up to 256 candidates (every real image, and most classes of the detection-rich benchmark): ONE warp, no CTA
+        // barrier at all.  Lane l keeps candidates l, l + 32, ... (packed key, normalised box, area) in registers; a round is
+        // two warp-reduce instructions for the winner, one shared-memory read of its decoded box, and the IoU tests ----
         if (warp != 0) return;
-        unsigned long long key = lane < n ? gkeys[lane] : 0ull;
-        key = warp_sort_desc(key, lane);
-        float4 orig = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < n) orig = gboxes[key_index(key)];
-        float area;
-        const float4 nb4 = norm_box(orig, area);
-        bool alive = lane < n;
+        float4 *s_box = reinterpret_cast<float4 *>(s_nms);   // decoded boxes by candidate position
+        unsigned long long pk[WARP_SLOTS];
+        float4 bx[WARP_SLOTS];
+        float ar[WARP_SLOTS];
+        unsigned alive = 0u;
+        unsigned long long tbest = 0ull;
+#pragma unroll
+        for (int s = 0; s < WARP_SLOTS; ++s) {
+            const int pos = lane + 32 * s;
+            pk[s] = 0ull;
+            bx[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ar[s] = 0.f;
+            if (pos < n) {
+                const unsigned long long k = gkeys[pos];
+                const float4 ob = gboxes[key_index(k)];
+                s_box[pos] = ob;
+                pk[s] = (k & 0xffffffff00000000ull) | ((unsigned long long)(0xFFFFFu - (unsigned)key_index(k)) << 12) | (unsigned long long)pos;
+                bx[s] = norm_box(ob, ar[s]);
+                alive |= 1u << s;
+                tbest = pk[s] > tbest ? pk[s] : tbest;
+            }
+        }
+        __syncwarp();
         int nsel = 0;
-        for (int i = 0; i < n && nsel < p.maxk; ++i) {
-            if (!((__ballot_sync(FULL, alive) >> i) & 1u)) continue;
-            float4 kb;
-            kb.x = __shfl_sync(FULL, nb4.x, i);
-            kb.y = __shfl_sync(FULL, nb4.y, i);
-            kb.z = __shfl_sync(FULL, nb4.z, i);
-            kb.w = __shfl_sync(FULL, nb4.w, i);
-            const float ka = __shfl_sync(FULL, area, i);
-            if (lane == i) {
-                write_det(out, nsel, key, orig);
-                alive = false;
-            } else if (lane > i && alive && iou_norm_gt(kb, ka, nb4, area, p.iou)) {
-                alive = false;
+        while (nsel < p.maxk) {
+            const unsigned hi = (unsigned)(tbest >> 32);
+            const unsigned mhi = __reduce_max_sync(FULL, hi);
+            const unsigned lo = (alive != 0u && hi == mhi) ? (unsigned)tbest : 0u;
+            const unsigned mlo = __reduce_max_sync(FULL, lo);
+            const unsigned long long w = ((unsigned long long)mhi << 32) | mlo;
+            if (w == 0ull) break;   // nothing alive (a live key is never 0: its index field is non-zero)
+            const float4 ob = s_box[(int)(w & 0xFFFull)];
+            float ka;
+            const float4 kb = norm_box(ob, ka);
+            if (lane == 0) {
+                k2y_det d;
+                d.ymin = ob.x;
+                d.xmin = ob.y;
+                d.ymax = ob.z;
+                d.xmax = ob.w;
+                d.score = __uint_as_float(mhi);
+                d.index = (int)(0xFFFFFu - (unsigned)((w >> 12) & 0xFFFFFull));
+                out[nsel] = d;
+            }
+            tbest = 0ull;
+#pragma unroll
+            for (int s = 0; s < WARP_SLOTS; ++s) {
+                if ((alive >> s) & 1u) {
+                    if (pk[s] == w || iou_norm_gt(kb, ka, bx[s], ar[s], p.iou)) alive &= ~(1u << s);
+                    else tbest = pk[s] > tbest ? pk[s] : tbest;
+                }
             }
             ++nsel;
         }

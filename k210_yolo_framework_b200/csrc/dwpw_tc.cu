@@ -113,6 +113,36 @@ __device__ __forceinline__ float dw_act_f(float v, int act, float alpha) {
     return v;
 }
 
+// 3x3 depthwise accumulation of one work unit: 4 vertically adjacent output pixels (rows 0..3 of the block) of one channel quad,
+// from a 6-row x 3-column window.  `base` points at the thread's top-left window pixel (128-byte lines, 128B-swizzled); WC (window
+// columns) is a template constant so that every load is `base + immediate + swz[c & 7]` — the line offset folds into the
+// instruction, the swizzle term comes from 8 per-thread constants (the pixel index mod 8 of tap c is (i + c) mod 8).
+template <int WC>
+__device__ __forceinline__ void dw_accumulate(const uint8_t *base, const uint32_t (&swz)[8], const float4 (&w9)[9], float4 (&acc)[4]) {
+#pragma unroll
+    for (int wy = 0; wy < 6; ++wy) {
+        float4 v[3];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int c = wy * WC + dx;
+            v[dx] = *reinterpret_cast<const float4 *>(base + c * 128 + swz[c & 7]);
+        }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int j = wy - dy;   // output row fed by this input row through tap row dy
+            if (j < 0 || j > 3) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 ww = w9[dy * 3 + dx];
+                acc[j].x = fmaf(v[dx].x, ww.x, acc[j].x);
+                acc[j].y = fmaf(v[dx].y, ww.y, acc[j].y);
+                acc[j].z = fmaf(v[dx].z, ww.z, acc[j].z);
+                acc[j].w = fmaf(v[dx].w, ww.w, acc[j].w);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(DP_THREADS, 1)
 dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_bhi,
                const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out, const DwPwParams p) {
@@ -270,7 +300,13 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         const int bx = q % p.tw, by = q / p.tw;
         const int i = lane >> 2, m = lane & 3;
         const int quad = 2 * m + hsel;     // channel quad inside a 32-channel chunk
-        const int WC = p.win_cols;
+        const int WC = p.win_cols;   // 10, 18 or 34 (8*tw + 2)
+        // the thread's top-left window pixel p0 = (4*by)*WC + 8*bx + i has p0 mod 8 == i (4*WC is a multiple of 8), so tap c = wy*WC + dx
+        // sits in line p0 + c whose swizzle phase is (i + c) mod 8
+        const uint32_t p0_bytes = (uint32_t)((by * 4) * WC + bx * 8 + i) * 128u;
+        uint32_t swz[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) swz[k] = (((uint32_t)quad) ^ ((uint32_t)(i + k) & 7u)) << 4;
         const bool tracer = warp == W_DW0 + 2 && lane == 0;
         mbar_wait(smem_u32(&bars->par_full), 0u);
         float4 w9[9];
@@ -304,28 +340,10 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                         float4 acc[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int wy = 0; wy < 6; ++wy) {
-                            float4 v[3];
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                const uint32_t pix = (uint32_t)((by * 4 + wy) * WC + bx * 8 + i + dx);
-                                v[dx] = *reinterpret_cast<const float4 *>(wptr + pix * 128u + ((((uint32_t)quad) ^ (pix & 7u)) << 4));
-                            }
-#pragma unroll
-                            for (int dy = 0; dy < 3; ++dy) {
-                                const int j = wy - dy;   // output row fed by this input row through tap row dy
-                                if (j < 0 || j > 3) continue;
-#pragma unroll
-                                for (int dx = 0; dx < 3; ++dx) {
-                                    const float4 ww = w9[dy * 3 + dx];
-                                    acc[j].x = fmaf(v[dx].x, ww.x, acc[j].x);
-                                    acc[j].y = fmaf(v[dx].y, ww.y, acc[j].y);
-                                    acc[j].z = fmaf(v[dx].z, ww.z, acc[j].z);
-                                    acc[j].w = fmaf(v[dx].w, ww.w, acc[j].w);
-                                }
-                            }
-                        }
+                        const uint8_t *tbase = wptr + p0_bytes;
+                        if (WC == 18) dw_accumulate<18>(tbase, swz, w9, acc);
+                        else if (WC == 10) dw_accumulate<10>(tbase, swz, w9, acc);
+                        else dw_accumulate<34>(tbase, swz, w9, acc);
                         const float *bnp = s_dw + 9 * p.cpad + cbase + quad * 4;
                         const float4 sc = *reinterpret_cast<const float4 *>(bnp);
                         const float4 sh = *reinterpret_cast<const float4 *>(bnp + p.cpad);
