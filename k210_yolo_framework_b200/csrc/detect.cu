@@ -137,6 +137,24 @@ __device__ __forceinline__ bool iou_norm_gt(const float4 a, float area_a, const 
     return __fdiv_rn(inter, uni) > thr;
 }
 
+// The same predicate as straight-line code (selects instead of early returns; the exact division only under a rarely-taken
+// branch): the register-resident NMS tests up to 8 candidates per thread per round, and with early-outs the compiler serialises
+// them (~190 cycles each) instead of interleaving the independent chains.
+__device__ __forceinline__ bool iou_norm_gt_sl(const float4 a, float area_a, const float4 b, float area_b, float thr) {
+    const float iy = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+    const float ix = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+    const float inter = __fmul_rn(iy, ix);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const float t = __fmul_rn(thr, uni);
+    const bool usable = thr >= 0.f && uni > 0.f;                       // the product form is only trusted then
+    const bool gt = usable && inter > __fmul_rn(t, 1.000001f);
+    const bool lt = usable && inter < __fmul_rn(t, 0.999999f);
+    bool res = gt;
+    if (!(gt || lt)) res = __fdiv_rn(inter, uni) > thr;                 // inside the margin (or degenerate): exact IEEE division
+    const bool degenerate = area_a <= 0.f || area_b <= 0.f;             // zero-area boxes: IoU 0
+    return degenerate ? (0.f > thr) : res;
+}
+
 // region_layer.c box_iou on centre-form (x,y,w,h) boxes (:228-254).
 __device__ __forceinline__ float overlap_c(float x1, float w1, float x2, float w2) {
     const float l1 = __fsub_rn(x1, __fmul_rn(w1, 0.5f));
@@ -543,13 +561,18 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
             d.index = index;
             out[nsel] = d;
         }
+        if (alive != 0u) {
+            unsigned kill = 0u;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+                kill |= (unsigned)(pk[s] == w || iou_norm_gt_sl(kb, ka, bx[s], ar[s], p.iou)) << s;
+            alive &= ~kill;
+        }
         tbest = 0ull;
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            if ((alive >> s) & 1u) {
-                if (pk[s] == w || iou_norm_gt(kb, ka, bx[s], ar[s], p.iou)) alive &= ~(1u << s);
-                else tbest = pk[s] > tbest ? pk[s] : tbest;
-            }
+            const unsigned long long cand = ((alive >> s) & 1u) ? pk[s] : 0ull;
+            tbest = cand > tbest ? cand : tbest;
         }
         ++nsel;
     }
@@ -628,13 +651,16 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
                 d.index = (int)(0xFFFFFu - (unsigned)((w >> 12) & 0xFFFFFull));
                 out[nsel] = d;
             }
+            unsigned kill = 0u;
+#pragma unroll
+            for (int s = 0; s < WARP_SLOTS; ++s)   // independent chains: dead / empty slots are tested too (their bits are masked)
+                kill |= (unsigned)(pk[s] == w || iou_norm_gt_sl(kb, ka, bx[s], ar[s], p.iou)) << s;
+            alive &= ~kill;
             tbest = 0ull;
 #pragma unroll
             for (int s = 0; s < WARP_SLOTS; ++s) {
-                if ((alive >> s) & 1u) {
-                    if (pk[s] == w || iou_norm_gt(kb, ka, bx[s], ar[s], p.iou)) alive &= ~(1u << s);
-                    else tbest = pk[s] > tbest ? pk[s] : tbest;
-                }
+                const unsigned long long cand = ((alive >> s) & 1u) ? pk[s] : 0ull;
+                tbest = cand > tbest ? cand : tbest;
             }
             ++nsel;
         }
