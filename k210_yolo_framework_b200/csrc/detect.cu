@@ -242,8 +242,9 @@ __device__ __forceinline__ BoxXform make_xform(const KerasParams &p, int b) {
     return x;
 }
 
-// tf_xywh_to_all (tools/utils.py:545-546) + correct_box (keras_inference.py:59-71) for one box; e = its (tx,ty,tw,th,..) record.
-__device__ __forceinline__ float4 decode_box(const KerasParams &p, const BoxXform &x, int box, const float *e) {
+// tf_xywh_to_all (tools/utils.py:545-546) + correct_box (keras_inference.py:59-71) for one box, on a record whose first four entries
+// already hold sigmoid(tx), sigmoid(ty), exp(tw), exp(th) (the scan kernel spreads those over all of its threads).
+__device__ __forceinline__ float4 assemble_box(const KerasParams &p, const BoxXform &x, int box, const float *e) {
     int l = 0;
     if (p.n_layers > 1 && box >= p.loff[1]) l = 1;
     if (p.n_layers > 2 && box >= p.loff[2]) l = 2;
@@ -252,11 +253,10 @@ __device__ __forceinline__ float4 decode_box(const KerasParams &p, const BoxXfor
     const int cell = local / p.A;
     const int W = p.lw[l];
     const int col = cell % W, row = cell / W;
-    const float tx = e[0], ty = e[1], tw = e[2], th = e[3];
-    const float bx = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)W);
-    const float by = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)p.lh[l]);
-    const float bw = __fmul_rn(exp_cr(tw), p.anchors[(l * p.A + a) * 2]);
-    const float bh = __fmul_rn(exp_cr(th), p.anchors[(l * p.A + a) * 2 + 1]);
+    const float bx = __fdiv_rn(__fadd_rn(e[0], (float)col), (float)W);
+    const float by = __fdiv_rn(__fadd_rn(e[1], (float)row), (float)p.lh[l]);
+    const float bw = __fmul_rn(e[2], p.anchors[(l * p.A + a) * 2]);
+    const float bh = __fmul_rn(e[3], p.anchors[(l * p.A + a) * 2 + 1]);
     const float cy = __fmul_rn(__fsub_rn(by, x.off_y), x.sc_y), cx = __fmul_rn(__fsub_rn(bx, x.off_x), x.sc_x);
     const float hh2 = __fdiv_rn(__fmul_rn(bh, x.sc_y), 2.0f), ww2 = __fdiv_rn(__fmul_rn(bw, x.sc_x), 2.0f);
     float4 r;
@@ -304,14 +304,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
     }
     __syncthreads();
     float *s_thr = s_conf + SCAN_BOXES;
+    // The five transcendentals of a box — sigmoid(tx), sigmoid(ty), exp(tw), exp(th), sigmoid(conf), each a correctly rounded
+    // (double precision) exponential — are spread over ALL threads (5 * nb items), written back in place of the raw values; with
+    // one thread per box the two warps doing the decode were the critical path of the CTA.
+    for (int it = tid; it < 5 * nb; it += SCAN_THREADS) {
+        const int i = it / 5, k = it - 5 * i;
+        float *e = s_rec + i * E + k;
+        const float t = *e;
+        float r;
+        if (k == 4) r = (t < p.logit_min) ? 0.f : sigmoidf_ref(t);   // 0 marks "no class can pass" (obj > 0 whenever the shortcut is on)
+        else if (k < 2) r = sigmoidf_ref(t);
+        else r = exp_cr(t);
+        *e = r;
+    }
+    __syncthreads();
     if (tid < nb) {
-        // sigmoid(conf) once per box; score = sigmoid(cls) * sigmoid(conf) <= sigmoid(conf), so a box whose objectness is
-        // below the threshold has no candidate in any class (0 marks it: obj > 0 whenever the shortcut is on).
-        // For the other boxes a class can only pass if sigmoid(cls) >= obj / sigmoid(conf), i.e. cls >= logit(obj / sc): a
-        // per-box logit bound (with a margin of 2e-3 (+0.2 %), thousands of float ulps of the sigmoid) rejects most
-        // (box, class) pairs with ONE comparison instead of a correctly rounded exponential.
-        const float t = s_rec[tid * E + 4];
-        const float sc = (t < p.logit_min) ? 0.f : sigmoidf_ref(t);
+        // score = sigmoid(cls) * sigmoid(conf) <= sigmoid(conf): a box whose objectness is below the threshold has no candidate
+        // in any class.  For the other boxes a class can only pass if sigmoid(cls) >= obj / sigmoid(conf), i.e. cls >=
+        // logit(obj / sc): a per-box logit bound (with a margin of 2e-3 (+0.2 %), thousands of float ulps of the sigmoid)
+        // rejects most (box, class) pairs with ONE comparison instead of a correctly rounded exponential.
+        const float sc = s_rec[tid * E + 4];
         s_conf[tid] = sc;
         float thr = p.logit_min;
         if (p.logit_min > -__int_as_float(0x7f800000) && sc >= p.obj) {
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
     } else if (tid >= SCAN_BOXES && tid < SCAN_BOXES + nb) {
         const int i = tid - SCAN_BOXES;
         const BoxXform x = make_xform(p, b);
-        p.boxes[(size_t)b * p.nbox + box0 + i] = decode_box(p, x, box0 + i, s_rec + i * E);
+        p.boxes[(size_t)b * p.nbox + box0 + i] = assemble_box(p, x, box0 + i, s_rec + i * E);
     }
     __syncthreads();
     const bool shortcut = p.logit_min > -__int_as_float(0x7f800000);
@@ -374,7 +386,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) detect_scan_kernel(const KerasPa
 // IoU test per live candidate, all candidates spread over the CTA's threads.  The selection order is exactly the order of
 // the sorted keys (score descending, index ascending), so the records equal the sequential algorithm's.
 constexpr int NMS_MAX_WARPS = 16;   // the kernel runs with 256 (cap <= 2048) or 512 threads
-constexpr int WARP_SLOTS = 8;       // candidates per lane of the single-warp path (<= 256 candidates)
 
 __device__ __forceinline__ void write_det(k2y_det *out, int slot, unsigned long long key, const float4 kb) {
     k2y_det d;
@@ -494,16 +505,17 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
     return nsel;
 }
 
-// Shared-memory path (n <= cap <= 4096): every thread keeps its candidates (position pos = tid + s * NMS_THREADS) in registers —
-// packed key, (min,max)-normalised box, area.  The packed key is (score bits << 32) | ((0xFFFFF - index) << 12) | pos: the low
-// 12 bits never decide a comparison (the (score, index) pair is unique), so ONE 64-bit maximum yields the winner and where its
-// box sits in shared memory.  A round: per-warp maximum (two warp-reduce instructions) -> one shared-memory atomicMax per
-// warp -> barrier -> everybody reads the winner and its box -> IoU tests of the own (register) candidates, unrolled.
+// Shared-memory rounds (CHUNK_MAX < n <= cap <= 4096): every thread keeps its candidates (packed key, (min,max)-normalised
+// box, area) in registers — position t + s * NMS_THREADS in slot s.  The packed key is (score bits << 32) | ((0xFFFFF - index)
+// << 12) | position: the low 12 bits never decide a comparison (the (score, index) pair is unique), so ONE 64-bit maximum yields
+// the winner AND where its decoded box sits in shared memory.  A round: per-warp maximum (two warp-reduce instructions) ->
+// shared memory -> barrier -> every warp reduces the per-warp maxima again -> winner's box from shared memory -> IoU tests of
+// the thread's own live candidates.  Work-efficient (maxk x n IoU tests), but maxk barrier-separated rounds.
 template <int NMS_THREADS, int SLOTS>
 __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, const unsigned long long *s_keys, const float4 *s_box,
                                                k2y_det *out, unsigned long long *s_best) {
     constexpr int NMS_WARPS = NMS_THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long pk[SLOTS];
     float4 bx[SLOTS];
     float ar[SLOTS];
@@ -517,19 +529,14 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
         ar[s] = 0.f;
         if (pos < n) {
             const unsigned long long k = s_keys[pos];
-            // (score, ~index) -> (score, 20-bit ~index, 12-bit position); + 1 in the position field keeps the key non-zero
             pk[s] = (k & 0xffffffff00000000ull) | ((unsigned long long)(0xFFFFFu - (unsigned)key_index(k)) << 12) | (unsigned long long)pos;
             bx[s] = norm_box(s_box[pos], ar[s]);
             alive |= 1u << s;
             tbest = pk[s] > tbest ? pk[s] : tbest;
         }
     }
-    const int warp = tid >> 5;
     int nsel = 0, par = 0;
     while (nsel < p.maxk) {
-        // per-warp maximum -> s_best[par][warp]; after the barrier every warp reduces the NMS_WARPS entries again (lane w holds
-        // warp w's): two warp-reduce instructions, no shared-memory atomics (a 64-bit atomicMax is a CAS loop that 16
-        // contending warps serialise)
         unsigned long long wmax = 0ull;
         if (__ballot_sync(FULL, alive != 0u) != 0u) {   // warps whose candidates are all dead only keep the barrier company
             const unsigned hi = (unsigned)(tbest >> 32);
@@ -546,37 +553,147 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
         const unsigned wlo = __reduce_max_sync(FULL, (unsigned)(mine >> 32) == whi ? (unsigned)mine : 0u);
         const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
         if (w == 0ull) break;   // nothing alive (a live key is never 0: its index field is non-zero)
-        const int wpos = (int)(w & 0xFFFull);
-        const float4 ob = s_box[wpos];       // as decoded (the record keeps these); every thread normalises its own copy
+        const float4 ob = s_box[(int)(w & 0xFFFull)];   // as decoded (the record keeps these); every thread normalises its own copy
         float ka;
         const float4 kb = norm_box(ob, ka);
         if (tid == 0) {
-            const int index = (int)(0xFFFFFu - (unsigned)((w >> 12) & 0xFFFFFull));
             k2y_det d;
             d.ymin = ob.x;
             d.xmin = ob.y;
             d.ymax = ob.z;
             d.xmax = ob.w;
             d.score = __uint_as_float((unsigned)(w >> 32));
-            d.index = index;
+            d.index = (int)(0xFFFFFu - (unsigned)((w >> 12) & 0xFFFFFull));
             out[nsel] = d;
-        }
-        if (alive != 0u) {
-            unsigned kill = 0u;
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-                kill |= (unsigned)(pk[s] == w || iou_norm_gt_sl(kb, ka, bx[s], ar[s], p.iou)) << s;
-            alive &= ~kill;
         }
         tbest = 0ull;
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            const unsigned long long cand = ((alive >> s) & 1u) ? pk[s] : 0ull;
-            tbest = cand > tbest ? cand : tbest;
+            if ((alive >> s) & 1u) {
+                if (pk[s] == w || iou_norm_gt(kb, ka, bx[s], ar[s], p.iou)) alive &= ~(1u << s);
+                else tbest = pk[s] > tbest ? pk[s] : tbest;
+            }
         }
         ++nsel;
     }
     return nsel;
+}
+
+// Chunked path (n <= CHUNK_MAX = 256 candidates, maxk <= CHUNK_MAXK): the usual case.  Greedy NMS keeps a candidate iff no
+// EARLIER KEPT candidate (in (score desc, index asc) order) overlaps it by more than the threshold, so with the candidates in
+// that order the serial dependence is between 32-candidate chunks, not between survivors:
+//   1. rank sort: thread t counts the keys above its own (n broadcast shared-memory reads) and scatters key + decoded box to
+//      that position — O(n^2) compares, trivial at n <= 256, no barrier-separated sort passes;
+//   2. warp c owns chunk c (sorted positions 32c .. 32c+31, one per lane) and computes, for its lane's candidate, the mask of
+//      the chunk's earlier lanes that would suppress it (32 IoU tests per lane, all warps in parallel);
+//   3. chunk steps c = 0 .. ceil(n/32)-1, one named barrier each: warp c resolves its chunk with warp votes alone — a lane is
+//      decided once every lane in its mask is decided, kept iff none of those is kept; the lowest undecided lane always
+//      qualifies, typical depth is 2-4 votes — appends the kept boxes to a shared list and leaves; the later warps test their
+//      candidate against the newly kept boxes only.  Every candidate still meets each survivor at most once (work n x maxk +
+//      32 n), but the barrier count drops from maxk (30) to n/32 (<= 8) and finished warps stop paying for them.
+// The IoU predicate and its argument order (survivor first) are those of the rounds path, so the decisions are the same bits.
+constexpr int CHUNK_MAX = 256;
+constexpr int CHUNK_MAXK = 64;
+struct ChunkShared {
+    unsigned long long skey[CHUNK_MAX];   // sorted keys
+    float4 sobox[CHUNK_MAX];              // sorted boxes as decoded
+    float4 snbox[CHUNK_MAX];              // ... (min,max)-normalised
+    float sarea[CHUNK_MAX];
+    float4 kbox[CHUNK_MAXK];              // survivors so far, normalised
+    float karea[CHUNK_MAXK];
+    int cnt[CHUNK_MAX / 32];              // survivors after chunk c
+};
+
+__device__ __forceinline__ void nms_chunked(const KerasParams &p, int n, const unsigned long long *gkeys, const float4 *gboxes,
+                                            k2y_det *out, int *count_out, unsigned long long *s_arrival, ChunkShared &cs) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = (n + 31) >> 5;
+    const bool valid = tid < n;
+    unsigned long long kt = 0ull;
+    float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        kt = gkeys[tid];
+        ob = gboxes[key_index(kt)];
+        s_arrival[tid] = kt;
+    }
+    __syncthreads();
+    if (warp >= nchunks) return;   // (warp-uniform) no candidate of this warp's own; the named barriers below count the rest
+    const int nact = nchunks * 32;
+    if (valid) {
+        int r = 0;
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) r += s_arrival[j] > kt ? 1 : 0;
+        cs.skey[r] = kt;
+        cs.sobox[r] = ob;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(nact) : "memory");
+    float ar = 0.f;
+    float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        kt = cs.skey[tid];
+        ob = cs.sobox[tid];
+        nb = norm_box(ob, ar);
+        cs.snbox[tid] = nb;
+        cs.sarea[tid] = ar;
+    }
+    __syncwarp();
+    // suppressors among the earlier lanes of the own chunk
+    unsigned sup = 0u;
+    {
+        const int c0 = warp * 32, m = min(32, n - c0);
+        for (int b = 0; b < m; ++b)
+            sup |= (unsigned)iou_norm_gt_sl(cs.snbox[c0 + b], cs.sarea[c0 + b], nb, ar, p.iou) << b;
+        sup &= (1u << lane) - 1u;
+    }
+    bool removed = !valid;
+    int base = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        if (warp == c) {
+            bool decided = removed, kept = false;
+            unsigned D = __ballot_sync(FULL, decided), K = 0u;
+            while (D != FULL) {
+                if (!decided && (sup & ~D) == 0u) {
+                    kept = (sup & K) == 0u;
+                    decided = true;
+                }
+                K = __ballot_sync(FULL, kept);
+                D = __ballot_sync(FULL, decided);
+            }
+            const int room = p.maxk - base;
+            const int slot = __popc(K & ((1u << lane) - 1u));
+            if (kept && slot < room) {
+                k2y_det d;
+                d.ymin = ob.x;
+                d.xmin = ob.y;
+                d.ymax = ob.z;
+                d.xmax = ob.w;
+                d.score = __uint_as_float((unsigned)(kt >> 32));
+                d.index = key_index(kt);
+                out[base + slot] = d;
+                cs.kbox[base + slot] = nb;
+                cs.karea[base + slot] = ar;
+            }
+            const int total = base + min(__popc(K), room);
+            if (lane == 0) {
+                cs.cnt[c] = total;
+                if (c == nchunks - 1 || total >= p.maxk) *count_out = total;
+            }
+        }
+        if (c == nchunks - 1) return;
+        // warps c .. nchunks-1 meet; warp c leaves afterwards (alternating barrier ids: the participant count changes every step)
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + (c & 1)), "r"((nchunks - c) * 32) : "memory");
+        if (warp == c) return;
+        const int total = cs.cnt[c];
+        if (!removed) {
+            for (int k = base; k < total; ++k)
+                if (iou_norm_gt(cs.kbox[k], cs.karea[k], nb, ar, p.iou)) {
+                    removed = true;
+                    break;
+                }
+        }
+        base = total;
+        if (base >= p.maxk) return;
+    }
 }
 
 // NMS_THREADS x SLOTS >= cap candidates of the shared-memory path: 256 threads for the common grids (every warp pays a fixed
@@ -589,6 +706,7 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
     extern __shared__ __align__(16) unsigned char s_nms[];
     __shared__ int s_red[2][NMS_MAX_WARPS][3];
     __shared__ unsigned long long s_best[2 * NMS_MAX_WARPS];
+    __shared__ ChunkShared s_chunk;
     pdl_trigger();
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
@@ -602,73 +720,11 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
     const unsigned long long *gkeys = p.keys + ((size_t)b * p.C + c) * p.P;
     const float4 *gboxes = p.boxes + (size_t)b * p.nbox;
 
-    if (n <= 32 * WARP_SLOTS && n <= p.cap && p.nbox < 0xFFFFF) {
-        // ---- up to 256 candidates (every real image, and most classes of the detection-rich benchmark): ONE warp, no CTA
-        // barrier at all.  Lane l keeps candidates l, l + 32, ... (packed key, normalised box, area) in registers; a round is
-        // two warp-reduce instructions for the winner, one shared-memory read of its decoded box, and the IoU tests ----
-        if (warp != 0) return;
-        float4 *s_box = reinterpret_cast<float4 *>(s_nms);   // decoded boxes by candidate position
-        unsigned long long pk[WARP_SLOTS];
-        float4 bx[WARP_SLOTS];
-        float ar[WARP_SLOTS];
-        unsigned alive = 0u;
-        unsigned long long tbest = 0ull;
-#pragma unroll
-        for (int s = 0; s < WARP_SLOTS; ++s) {
-            const int pos = lane + 32 * s;
-            pk[s] = 0ull;
-            bx[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ar[s] = 0.f;
-            if (pos < n) {
-                const unsigned long long k = gkeys[pos];
-                const float4 ob = gboxes[key_index(k)];
-                s_box[pos] = ob;
-                pk[s] = (k & 0xffffffff00000000ull) | ((unsigned long long)(0xFFFFFu - (unsigned)key_index(k)) << 12) | (unsigned long long)pos;
-                bx[s] = norm_box(ob, ar[s]);
-                alive |= 1u << s;
-                tbest = pk[s] > tbest ? pk[s] : tbest;
-            }
-        }
-        __syncwarp();
-        int nsel = 0;
-        while (nsel < p.maxk) {
-            const unsigned hi = (unsigned)(tbest >> 32);
-            const unsigned mhi = __reduce_max_sync(FULL, hi);
-            const unsigned lo = (alive != 0u && hi == mhi) ? (unsigned)tbest : 0u;
-            const unsigned mlo = __reduce_max_sync(FULL, lo);
-            const unsigned long long w = ((unsigned long long)mhi << 32) | mlo;
-            if (w == 0ull) break;   // nothing alive (a live key is never 0: its index field is non-zero)
-            const float4 ob = s_box[(int)(w & 0xFFFull)];
-            float ka;
-            const float4 kb = norm_box(ob, ka);
-            if (lane == 0) {
-                k2y_det d;
-                d.ymin = ob.x;
-                d.xmin = ob.y;
-                d.ymax = ob.z;
-                d.xmax = ob.w;
-                d.score = __uint_as_float(mhi);
-                d.index = (int)(0xFFFFFu - (unsigned)((w >> 12) & 0xFFFFFull));
-                out[nsel] = d;
-            }
-            unsigned kill = 0u;
-#pragma unroll
-            for (int s = 0; s < WARP_SLOTS; ++s)   // independent chains: dead / empty slots are tested too (their bits are masked)
-                kill |= (unsigned)(pk[s] == w || iou_norm_gt_sl(kb, ka, bx[s], ar[s], p.iou)) << s;
-            alive &= ~kill;
-            tbest = 0ull;
-#pragma unroll
-            for (int s = 0; s < WARP_SLOTS; ++s) {
-                const unsigned long long cand = ((alive >> s) & 1u) ? pk[s] : 0ull;
-                tbest = cand > tbest ? cand : tbest;
-            }
-            ++nsel;
-        }
-        if (lane == 0) *count_out = nsel;
+    int nsel;
+    if (n <= CHUNK_MAX && p.maxk <= CHUNK_MAXK) {
+        nms_chunked(p, n, gkeys, gboxes, out, count_out, reinterpret_cast<unsigned long long *>(s_nms), s_chunk);
         return;
     }
-
-    int nsel;
     if (n <= p.cap) {
         // keys and decoded boxes of all candidates in shared memory (arrival order: no sort needed)
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_nms);
