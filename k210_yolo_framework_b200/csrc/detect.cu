@@ -505,8 +505,8 @@ __device__ __forceinline__ int nms_rounds(const KerasParams &p, int n, const uns
     return nsel;
 }
 
-// Shared-memory rounds (CHUNK_MAX < n <= cap <= 4096): every thread keeps its candidates (packed key, (min,max)-normalised
-// box, area) in registers — position t + s * NMS_THREADS in slot s.  The packed key is (score bits << 32) | ((0xFFFFF - index)
+// Shared-memory rounds (CHUNK_MAX < n <= cap <= 4096): every thread keeps the packed keys of its candidates in registers —
+// position t + s * NMS_THREADS in slot s; their boxes stay in shared memory (the register budget decides how many CTAs fit an SM).  The packed key is (score bits << 32) | ((0xFFFFF - index)
 // << 12) | position: the low 12 bits never decide a comparison (the (score, index) pair is unique), so ONE 64-bit maximum yields
 // the winner AND where its decoded box sits in shared memory.  A round: per-warp maximum (two warp-reduce instructions) ->
 // shared memory -> barrier -> every warp reduces the per-warp maxima again -> winner's box from shared memory -> IoU tests of
@@ -517,20 +517,15 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
     constexpr int NMS_WARPS = NMS_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long pk[SLOTS];
-    float4 bx[SLOTS];
-    float ar[SLOTS];
     unsigned alive = 0u;
     unsigned long long tbest = 0ull;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         const int pos = tid + s * NMS_THREADS;
         pk[s] = 0ull;
-        bx[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ar[s] = 0.f;
         if (pos < n) {
             const unsigned long long k = s_keys[pos];
             pk[s] = (k & 0xffffffff00000000ull) | ((unsigned long long)(0xFFFFFu - (unsigned)key_index(k)) << 12) | (unsigned long long)pos;
-            bx[s] = norm_box(s_box[pos], ar[s]);
             alive |= 1u << s;
             tbest = pk[s] > tbest ? pk[s] : tbest;
         }
@@ -570,7 +565,9 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
             if ((alive >> s) & 1u) {
-                if (pk[s] == w || iou_norm_gt(kb, ka, bx[s], ar[s], p.iou)) alive &= ~(1u << s);
+                float ar;
+                const float4 bx = norm_box(s_box[tid + s * NMS_THREADS], ar);   // from shared memory: 2 registers per slot, not 7
+                if (pk[s] == w || iou_norm_gt(kb, ka, bx, ar, p.iou)) alive &= ~(1u << s);
                 else tbest = pk[s] > tbest ? pk[s] : tbest;
             }
         }
@@ -582,131 +579,227 @@ __device__ __forceinline__ int nms_rounds_smem(const KerasParams &p, int n, cons
 // Chunked path (n <= CHUNK_MAX = 256 candidates, maxk <= CHUNK_MAXK): the usual case.  Greedy NMS keeps a candidate iff no
 // EARLIER KEPT candidate (in (score desc, index asc) order) overlaps it by more than the threshold, so with the candidates in
 // that order the serial dependence is between 32-candidate chunks, not between survivors:
-//   1. rank sort: thread t counts the keys above its own (n broadcast shared-memory reads) and scatters key + decoded box to
-//      that position — O(n^2) compares, trivial at n <= 256, no barrier-separated sort passes;
-//   2. warp c owns chunk c (sorted positions 32c .. 32c+31, one per lane) and computes, for its lane's candidate, the mask of
-//      the chunk's earlier lanes that would suppress it (32 IoU tests per lane, all warps in parallel);
-//   3. chunk steps c = 0 .. ceil(n/32)-1, one named barrier each: warp c resolves its chunk with warp votes alone — a lane is
-//      decided once every lane in its mask is decided, kept iff none of those is kept; the lowest undecided lane always
-//      qualifies, typical depth is 2-4 votes — appends the kept boxes to a shared list and leaves; the later warps test their
-//      candidate against the newly kept boxes only.  Every candidate still meets each survivor at most once (work n x maxk +
-//      32 n), but the barrier count drops from maxk (30) to n/32 (<= 8) and finished warps stop paying for them.
-// The IoU predicate and its argument order (survivor first) are those of the rounds path, so the decisions are the same bits.
+//   1. rank sort: two lanes per candidate (l, l ^ 16 of one warp) count the keys <= its own, half of the list each — broadcast
+//      16-byte shared-memory reads, three carry-chain integer instructions per 64-bit compare — add their counts with one
+//      shuffle and scatter key / decoded + normalised box to that position: O(n^2) compares, trivial at n <= 256, and no
+//      barrier-separated sort passes;
+//   2. chunk c = sorted positions 32c .. 32c+31 belongs to warps c and 8+c, one member per lane.  Every unordered pair of a
+//      chunk is tested ONCE (the predicate is symmetric bit for bit: min/max/+ commute): member q meets q+1 .. q+16 (mod 32),
+//      warp c the distances 1-8, warp 8+c 9-16; one vote per distance hands every lane the hits of the whole warp, from which
+//      it assembles its own row ("whom do I suppress": later members only).  Warp 8+c passes its half through shared memory
+//      (a 64-thread named barrier per chunk) and leaves;
+//   3. chunk steps c = 0 .. ceil(n/32)-1 on warp c: starting from the members already removed by earlier chunks, repeatedly
+//      keep the first member still standing and remove its row (one find-first-set + one shuffle per SURVIVOR, <= maxk over
+//      the whole class); the kept boxes go to a shared list, the warp ARRIVES at the step's named barrier and leaves; the
+//      later warps wait on it and test their candidate against the newly kept boxes only (four independent tests at a time).
+//      Every candidate still meets each survivor at most once (work n x maxk + 16 n tests), but the barrier count drops from
+//      maxk (30) to n/32 (<= 8) and finished warps stop paying.
+// The IoU predicate is that of the rounds path, so the decisions are the same bits.  Needs blockDim.x == 2 * CHUNK_MAX.
 constexpr int CHUNK_MAX = 256;
 constexpr int CHUNK_MAXK = 64;
-struct ChunkShared {
+#ifdef K2Y_NMS_TRACE   // development aid: phase clocks of the dense classes of image 0, printed per warp
+#define NMS_T(i) do { if (lane == 0) tr[i] = clock64(); } while (0)
+#else
+#define NMS_T(i) do { } while (0)
+#endif
+struct __align__(16) ChunkShared {
     unsigned long long skey[CHUNK_MAX];   // sorted keys
     float4 sobox[CHUNK_MAX];              // sorted boxes as decoded
     float4 snbox[CHUNK_MAX];              // ... (min,max)-normalised
     float sarea[CHUNK_MAX];
-    float4 kbox[CHUNK_MAXK];              // survivors so far, normalised
-    float karea[CHUNK_MAXK];
+    unsigned rows[CHUNK_MAX];             // warp 8+c's half of the rows of chunk c
+    float4 kbox[CHUNK_MAXK + 4];          // survivors so far, normalised (+4: the test loop reads in groups of four)
+    float karea[CHUNK_MAXK + 4];
     int cnt[CHUNK_MAX / 32];              // survivors after chunk c
 };
+constexpr size_t CHUNK_SMEM = (CHUNK_MAX + 4) * sizeof(unsigned long long) + sizeof(ChunkShared);   // arrival keys (padded to x4), tables
+
+// r += (a >= b) for 64-bit keys given as 32-bit halves: the borrow chain of a - b, its final carry added to r
+__device__ __forceinline__ void count_ge(unsigned &r, unsigned alo, unsigned ahi, unsigned blo, unsigned bhi) {
+    asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %3;\n\tsubc.cc.u32 t, %2, %4;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(r) : "r"(alo), "r"(ahi), "r"(blo), "r"(bhi));
+}
+
+// named barriers with immediate ids (a register id makes ptxas reserve all 16 barriers for the CTA)
+#define K2Y_BAR_CASE(op, i) case i: asm volatile(op " " #i ", %0;" ::"r"(count) : "memory"); break;
+#define K2Y_BAR_SWITCH(op)                                                                                                  \
+    switch (id) {                                                                                                           \
+        K2Y_BAR_CASE(op, 1) K2Y_BAR_CASE(op, 2) K2Y_BAR_CASE(op, 3) K2Y_BAR_CASE(op, 4) K2Y_BAR_CASE(op, 5) K2Y_BAR_CASE(op, 6) \
+        K2Y_BAR_CASE(op, 7) K2Y_BAR_CASE(op, 8) K2Y_BAR_CASE(op, 9) K2Y_BAR_CASE(op, 10) K2Y_BAR_CASE(op, 11)                   \
+        default: break;                                                                                                     \
+    }
+__device__ __forceinline__ void named_sync(int id, int count) { K2Y_BAR_SWITCH("bar.sync") }
+__device__ __forceinline__ void named_arrive(int id, int count) { K2Y_BAR_SWITCH("bar.arrive") }
 
 __device__ __forceinline__ void nms_chunked(const KerasParams &p, int n, const unsigned long long *gkeys, const float4 *gboxes,
                                             k2y_det *out, int *count_out, unsigned long long *s_arrival, ChunkShared &cs) {
+    constexpr int HW = CHUNK_MAX / 32;   // warps 0..7 own the chunks, warps 8..15 help with the pair tests
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunks = (n + 31) >> 5;
-    const bool valid = tid < n;
-    unsigned long long kt = 0ull;
-    float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-        kt = gkeys[tid];
-        ob = gboxes[key_index(kt)];
-        s_arrival[tid] = kt;
-    }
-    __syncthreads();
-    if (warp >= nchunks) return;   // (warp-uniform) no candidate of this warp's own; the named barriers below count the rest
-    const int nact = nchunks * 32;
-    if (valid) {
-        int r = 0;
-#pragma unroll 8
-        for (int j = 0; j < n; ++j) r += s_arrival[j] > kt ? 1 : 0;
-        cs.skey[r] = kt;
-        cs.sobox[r] = ob;
-    }
-    asm volatile("bar.sync 1, %0;" ::"r"(nact) : "memory");
-    float ar = 0.f;
-    float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-        kt = cs.skey[tid];
-        ob = cs.sobox[tid];
-        nb = norm_box(ob, ar);
-        cs.snbox[tid] = nb;
-        cs.sarea[tid] = ar;
-    }
-    __syncwarp();
-    // suppressors among the earlier lanes of the own chunk
-    unsigned sup = 0u;
+#ifdef K2Y_NMS_TRACE
+    long long tr[16];
+    for (int i = 0; i < 16; ++i) tr[i] = 0;
+#endif
+    NMS_T(0);
+    // phase 1: warp w, lanes l and l ^ 16 <-> candidate 16 w + (l & 15)
+    const int half = lane >> 4, ci = warp * 16 + (lane & 15);
+    const bool cvalid = ci < n;
+    const int L = (n + 3) & ~3;   // arrival list padded with zero keys (below every real key) to a multiple of four
     {
-        const int c0 = warp * 32, m = min(32, n - c0);
-        for (int b = 0; b < m; ++b)
-            sup |= (unsigned)iou_norm_gt_sl(cs.snbox[c0 + b], cs.sarea[c0 + b], nb, ar, p.iou) << b;
-        sup &= (1u << lane) - 1u;
+        unsigned long long kt = 0ull;
+        float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cvalid) {
+            kt = gkeys[ci];
+            if (half) ob = gboxes[key_index(kt)];
+        }
+        if (!half && ci < L) s_arrival[ci] = kt;
+        __syncthreads();
+        NMS_T(1);
+        const bool ranks = warp * 16 < n, pairs_too = (warp < HW ? warp : warp - HW) < nchunks;
+        if (!ranks && !pairs_too) return;   // (warp-uniform) the named barrier below counts the warps that stay
+        if (ranks) {
+            // keys <= own among entries [j0, j0 + L/2); sorted position = L - (count of both halves): pads and the key itself count
+            const int j0 = half ? (L >> 1) : 0;
+            const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(s_arrival + j0);
+            const unsigned klo = (unsigned)kt, khi = (unsigned)(kt >> 32);
+            unsigned cnt = 0u;
+#pragma unroll 4
+            for (int j = 0; j < (L >> 2); ++j) {
+                const ulonglong2 v = pairs[j];
+                count_ge(cnt, klo, khi, (unsigned)v.x, (unsigned)(v.x >> 32));
+                count_ge(cnt, klo, khi, (unsigned)v.y, (unsigned)(v.y >> 32));
+            }
+            cnt += __shfl_xor_sync(FULL, cnt, 16);
+            const int r = L - (int)cnt;
+            if (cvalid) {
+                if (half) {
+                    float ar;
+                    const float4 nb = norm_box(ob, ar);
+                    cs.sobox[r] = ob;
+                    cs.snbox[r] = nb;
+                    cs.sarea[r] = ar;
+                } else {
+                    cs.skey[r] = kt;
+                }
+            }
+        }
+        NMS_T(2);
+        int staying = 0;
+        for (int w = 0; w < 2 * HW; ++w) staying += (w * 16 < n || (w < HW ? w : w - HW) < nchunks) ? 32 : 0;
+        named_sync(1, staying);
+        NMS_T(3);
     }
+    // phase 2: warps c and 8+c, lane q <-> sorted candidate 32 c + q
+    const int c_own = warp < HW ? warp : warp - HW;
+    if (c_own >= nchunks) return;
+    const int si = 32 * c_own + lane;
+    const bool valid = si < n;
+    float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ar = 0.f;
+    if (valid) {
+        nb = cs.snbox[si];
+        ar = cs.sarea[si];
+    }
+    unsigned myrow = 0u;   // later members of the chunk that this one suppresses
+    {
+        const int d0 = warp < HW ? 0 : 8;
+#pragma unroll
+        for (int u = 1; u <= 8; ++u) {
+            const int d = d0 + u, b = (lane + d) & 31;
+            bool hit = iou_norm_gt_sl(cs.snbox[32 * c_own + b], cs.sarea[32 * c_own + b], nb, ar, p.iou);
+            hit = hit && valid && 32 * c_own + b < n && !(d == 16 && lane >= 16);   // distance 16: from the lower member only
+            const unsigned T = __ballot_sync(FULL, hit);   // bit q: members q and (q + d) & 31 overlap
+            if (lane + d < 32) myrow |= ((T >> lane) & 1u) << (lane + d);   // my own test, partner above me
+            if (lane < d) myrow |= T & (1u << (lane + 32 - d));              // the test of member lane + 32 - d wrapped around to me
+        }
+    }
+    if (warp >= HW) {
+        cs.rows[si] = myrow;
+        __threadfence_block();
+        named_arrive(4 + c_own, 64);
+        return;
+    }
+    NMS_T(4);
+    named_sync(4 + c_own, 64);
+    myrow |= cs.rows[si];
+    // phase 3
     bool removed = !valid;
     int base = 0;
     for (int c = 0; c < nchunks; ++c) {
+        const int nthr = (nchunks - c) * 32;   // warps c .. nchunks-1 meet at this step's barrier (ids alternate: the count changes)
         if (warp == c) {
-            bool decided = removed, kept = false;
-            unsigned D = __ballot_sync(FULL, decided), K = 0u;
-            while (D != FULL) {
-                if (!decided && (sup & ~D) == 0u) {
-                    kept = (sup & K) == 0u;
-                    decided = true;
-                }
-                K = __ballot_sync(FULL, kept);
-                D = __ballot_sync(FULL, decided);
-            }
+            NMS_T(5);
+            unsigned R = __ballot_sync(FULL, removed), K = 0u;
             const int room = p.maxk - base;
+            int count = 0;
+            while (R != FULL && count < room) {
+                const int b = __ffs(~R) - 1;   // first member still standing: kept; it removes its row
+                K |= 1u << b;
+                ++count;
+                R |= (1u << b) | __shfl_sync(FULL, myrow, b);
+            }
+            const bool kept = (K >> lane) & 1u;
             const int slot = __popc(K & ((1u << lane) - 1u));
-            if (kept && slot < room) {
-                k2y_det d;
-                d.ymin = ob.x;
-                d.xmin = ob.y;
-                d.ymax = ob.z;
-                d.xmax = ob.w;
-                d.score = __uint_as_float((unsigned)(kt >> 32));
-                d.index = key_index(kt);
-                out[base + slot] = d;
+            const int total = base + count;
+            if (kept) {
                 cs.kbox[base + slot] = nb;
                 cs.karea[base + slot] = ar;
             }
-            const int total = base + min(__popc(K), room);
-            if (lane == 0) {
-                cs.cnt[c] = total;
-                if (c == nchunks - 1 || total >= p.maxk) *count_out = total;
+            if (lane == 0) cs.cnt[c] = total;
+            if (c < nchunks - 1) {
+                __threadfence_block();
+                named_arrive(2 + (c & 1), nthr);
             }
+            if (kept) {
+                const unsigned long long k = cs.skey[si];
+                const float4 o = cs.sobox[si];
+                k2y_det d;
+                d.ymin = o.x;
+                d.xmin = o.y;
+                d.ymax = o.z;
+                d.xmax = o.w;
+                d.score = __uint_as_float((unsigned)(k >> 32));
+                d.index = key_index(k);
+                out[base + slot] = d;
+            }
+            if (lane == 0 && (c == nchunks - 1 || total >= p.maxk)) *count_out = total;
+            NMS_T(6);
+#ifdef K2Y_NMS_TRACE
+            if (lane == 0 && blockIdx.y == 0 && n > 128)
+                printf("nms-trace class %d n %d chunk %d/%d base %d: load %lld rank %lld bar %lld pairs %lld wait %lld resolve %lld total %lld\n",
+                       (int)blockIdx.x, n, c, nchunks, base, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4],
+                       tr[6] - tr[5], tr[6] - tr[0]);
+#endif
+            return;
         }
-        if (c == nchunks - 1) return;
-        // warps c .. nchunks-1 meet; warp c leaves afterwards (alternating barrier ids: the participant count changes every step)
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + (c & 1)), "r"((nchunks - c) * 32) : "memory");
-        if (warp == c) return;
+        named_sync(2 + (c & 1), nthr);
         const int total = cs.cnt[c];
         if (!removed) {
-            for (int k = base; k < total; ++k)
-                if (iou_norm_gt(cs.kbox[k], cs.karea[k], nb, ar, p.iou)) {
+            // against the survivors of chunk c, four independent straight-line tests at a time (entries past `total` are ignored)
+            for (int k = base; k < total; k += 4) {
+                bool hit = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    hit |= iou_norm_gt_sl(cs.kbox[k + u], cs.karea[k + u], nb, ar, p.iou) && (k + u < total);
+                if (hit) {
                     removed = true;
                     break;
                 }
+            }
         }
         base = total;
         if (base >= p.maxk) return;
     }
 }
 
-// NMS_THREADS x SLOTS >= cap candidates of the shared-memory path: 256 threads for the common grids (every warp pays a fixed
-// per-round cost — reduce, barrier, winner look-up — whether or not it still has live candidates, so fewer, fuller warps win:
-// 28 -> ... us on the cfg-2 bench workload), 512 only for cap > 2048.  One kernel per pair so that the small grids are not
-// compiled at the register count of the largest.
+// 512 threads: two lanes per candidate in the chunked path's sort / mask phases, NMS_THREADS x SLOTS >= cap candidates in the
+// rounds path (4 slots up to 2048 candidates, 8 beyond: one instantiation each, so that the common grids are not compiled at
+// the register count of the largest).
 template <int NMS_THREADS, int SLOTS>
-__global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasParams p) {
+__global__ void __launch_bounds__(NMS_THREADS, 2) detect_nms_kernel(const KerasParams p) {
     constexpr int NMS_WARPS = NMS_THREADS / 32;
     extern __shared__ __align__(16) unsigned char s_nms[];
     __shared__ int s_red[2][NMS_MAX_WARPS][3];
     __shared__ unsigned long long s_best[2 * NMS_MAX_WARPS];
-    __shared__ ChunkShared s_chunk;
     pdl_trigger();
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
@@ -721,8 +814,10 @@ __global__ void __launch_bounds__(NMS_THREADS) detect_nms_kernel(const KerasPara
     const float4 *gboxes = p.boxes + (size_t)b * p.nbox;
 
     int nsel;
-    if (n <= CHUNK_MAX && p.maxk <= CHUNK_MAXK) {
-        nms_chunked(p, n, gkeys, gboxes, out, count_out, reinterpret_cast<unsigned long long *>(s_nms), s_chunk);
+    if (NMS_THREADS == 2 * CHUNK_MAX && n <= CHUNK_MAX && p.maxk <= CHUNK_MAXK) {
+        // dynamic region = [CHUNK_MAX + 4] arrival-order keys, then the chunk tables (the launch provides at least CHUNK_SMEM bytes)
+        nms_chunked(p, n, gkeys, gboxes, out, count_out, reinterpret_cast<unsigned long long *>(s_nms),
+                    *reinterpret_cast<ChunkShared *>(s_nms + (CHUNK_MAX + 4) * sizeof(unsigned long long)));
         return;
     }
     if (n <= p.cap) {
@@ -1057,13 +1152,12 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     p.alive_stride = (int)L.alive_stride;
     const size_t scan_smem = (size_t)SCAN_BOXES * (5 + p.C + 2) * sizeof(float);
     p.c_magic = (unsigned)((0x100000000ull + (unsigned long long)p.C - 1ull) / (unsigned long long)p.C);
-    const size_t nms_smem = (size_t)p.cap * 24;  // keys + decoded boxes
+    const size_t nms_smem = std::max((size_t)p.cap * 24, CHUNK_SMEM);  // keys + decoded boxes | the chunked path's tables
     int dev = 0;
     K2Y_CUDA_CHECK(cudaGetDevice(&dev));
     static bool attr_set[64] = {false};  // per device: opt-in shared memory is a per-device function attribute
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 24));
-        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 24));
+        K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 24));
         K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_nms_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_CAP * 24));
         K2Y_CUDA_CHECK(cudaFuncSetAttribute(detect_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set[dev] = true;
@@ -1077,8 +1171,7 @@ extern "C" int k2y_detect_keras_strided(const k2y_detect_cfg *cfg, const float *
     dim3 sgrid((p.nbox + SCAN_BOXES - 1) / SCAN_BOXES, batch);
     detect_scan_kernel<<<sgrid, SCAN_THREADS, scan_smem, st>>>(p);  // follows a memset: plain stream order
     K2Y_CUDA_CHECK(cudaGetLastError());
-    if (p.cap <= 1024) launch_k(detect_nms_kernel<256, 4>, dim3(p.C, batch), dim3(256), nms_smem, st, p);
-    else if (p.cap <= 2048) launch_k(detect_nms_kernel<256, 8>, dim3(p.C, batch), dim3(256), nms_smem, st, p);
+    if (p.cap <= 2048) launch_k(detect_nms_kernel<512, 4>, dim3(p.C, batch), dim3(512), nms_smem, st, p);
     else launch_k(detect_nms_kernel<512, 8>, dim3(p.C, batch), dim3(512), nms_smem, st, p);
     K2Y_CUDA_CHECK(cudaGetLastError());
     return K2Y_OK;
