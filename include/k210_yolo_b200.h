@@ -94,6 +94,10 @@ int k2y_net_bind_u8(k2y_net *net, const unsigned char *x_u8_dev, int32_t *img_ma
  * graph is kept per (batch, input buffer), so alternating between two input buffers (H2D of batch i+1 while batch i runs)
  * costs nothing after the first use of each.  k2y_net_bind_u8 behaves the same way for the uint8 input. */
 int k2y_net_bind_input(k2y_net *net, const float *x_dev);
+/* Re-points the head outputs at another set of device buffers (same shapes as in k2y_net_bind).  One CUDA graph is kept per
+ * (batch, input buffer, first head buffer): alternating between two head sets lets the decode/NMS of batch i (reading set A on
+ * another stream) overlap the convolutions of batch i+1 (writing set B) at no re-capture cost. */
+int k2y_net_bind_heads(k2y_net *net, float *const *heads_dev, int n_heads);
 /* predict on bound device buffers (keras_inference.py:88), asynchronous on `stream`. */
 int k2y_net_run(k2y_net *net, int batch, void *stream);
 /* predict with HOST buffers: H2D of x, run, D2H of every head, stream-synchronised on return.

@@ -95,7 +95,7 @@ struct k2y_net {
     std::vector<float *> heads_dev;
     // one captured graph per (batch, input binding): re-binding the input to an alternate buffer (double-buffered H2D) reuses
     // the graph captured for that buffer instead of re-capturing
-    std::map<std::tuple<int, const void *, const void *, const void *>, cudaGraphExec_t> graphs;
+    std::map<std::tuple<int, const void *, const void *, const void *, const void *>, cudaGraphExec_t> graphs;  // (batch, x, x_u8, img_max, head 0)
     int last_batch = 0;
     int launches = 0;  // kernels issued by the last issue_layers() pass
     float *tc_scratch = nullptr;   // this net's split-K partials (never shared with another net / stream)
@@ -977,6 +977,25 @@ extern "C" int k2y_net_bind_input(k2y_net *net, const float *x_dev) {
     return K2Y_OK;
 }
 
+extern "C" int k2y_net_bind_heads(k2y_net *net, float *const *heads_dev, int n_heads) {
+    if (check_net(net, "k2y_net_bind_heads")) return K2Y_ERR_INVALID;
+    if (!net->bound) {
+        set_error("k2y_net_bind_heads: call k2y_net_bind first");
+        return K2Y_ERR_STATE;
+    }
+    if (!heads_dev || n_heads != (int)net->outputs.size()) {
+        set_error("k2y_net_bind_heads: null pointer or wrong number of heads (%d, expected %zu)", n_heads, net->outputs.size());
+        return K2Y_ERR_INVALID;
+    }
+    for (int l = 0; l < n_heads; ++l)
+        if (!heads_dev[l] || ((uintptr_t)heads_dev[l] & 15) != 0) {
+            set_error("k2y_net_bind_heads: head buffers must be non-null and 16-byte aligned");
+            return K2Y_ERR_INVALID;
+        }
+    net->heads_dev.assign(heads_dev, heads_dev + n_heads);
+    return K2Y_OK;
+}
+
 extern "C" int k2y_net_run(k2y_net *net, int batch, void *stream) {
     if (check_net(net, "k2y_net_run")) return K2Y_ERR_INVALID;
     if (!net->finalized || !net->bound) {
@@ -991,7 +1010,8 @@ extern "C" int k2y_net_run(k2y_net *net, int batch, void *stream) {
     DeviceGuard guard(net->device);
     net->last_batch = batch;
     if (!net->use_graph) return issue_layers(net, batch, st);
-    const auto key = std::make_tuple(batch, (const void *)net->x_dev, (const void *)net->x_u8, (const void *)net->img_max);
+    const auto key = std::make_tuple(batch, (const void *)net->x_dev, (const void *)net->x_u8, (const void *)net->img_max,
+                                     (const void *)net->heads_dev[0]);
     auto it = net->graphs.find(key);
     if (it == net->graphs.end()) {
         cudaGraph_t g = nullptr;

@@ -6,10 +6,14 @@ job spans several GPUs] -> D2H of the fixed-size record blocks.  ``step_device()
 already resident in HBM (what ``bench.py``'s ``value`` times).  ``submit``/``collect`` is the streaming form.
 It is the batched form of keras_inference.py:87-135, which the reference runs for one image per process.
 
-Streams: kernels run on the caller's current stream.  With more than one rank the all-gather (and the D2H copy of
-the gathered blocks) runs on a side stream into one of two gather buffers, so the collective of batch i overlaps the
-convolutions of batch i+1; H2D copies use a third stream and land directly in one of two device input buffers the
-network is re-pointed at (one CUDA graph per buffer), so there is no staging copy.
+Streams: the network (one CUDA graph) runs on the caller's current stream; decode + NMS run on a second, high-priority
+stream and read one of TWO head-buffer sets the network alternates between, so the decode of batch i overlaps the first
+convolutions of batch i+1 (the small-grid layers leave SMs idle; the decode kernels are latency-bound).  With more than one
+rank the all-gather (and the D2H copy of the gathered blocks) runs on a third stream into one of two gather buffers; H2D
+copies use a fourth stream and land directly in one of two device input buffers the network is re-pointed at (one CUDA graph
+per (input buffer, head set)), so there is no staging copy.  ``step_device(pipelined=False)`` (the default) makes the
+caller's stream wait for the decode before returning — plain stream semantics; the streaming calls (``submit``/``collect``,
+``step_device(pipelined=True)`` + ``wait_gathered()``) keep the overlap.
 """
 from __future__ import annotations
 
@@ -43,6 +47,9 @@ class DetectionPipeline:
                                       slots=SLOTS)
         self._img_hw = torch.tensor([[image_size[0], image_size[1]]] * batch, dtype=torch.float32, device=dev)
         self._side = torch.cuda.Stream(device=dev)          # all-gather + D2H of gathered blocks
+        self._det_stream = torch.cuda.Stream(device=dev, priority=-1)   # decode + NMS (its CTAs go first when SM slots free up)
+        self._head_sets = None                              # two sets of head buffers, created on first use
+        self._heads_ready = [torch.cuda.Event() for _ in range(SLOTS)]   # network finished writing head set
         self._copy_stream = torch.cuda.Stream(device=dev)   # H2D
         self._host = [torch.empty(self.gather.bufs[0].shape, dtype=torch.int32).pin_memory() for _ in range(SLOTS)]
         self._in_f32: Optional[List[torch.Tensor]] = None   # device input buffers of the streaming API, created on first use
@@ -63,34 +70,47 @@ class DetectionPipeline:
 
     # -- device-resident step ---------------------------------------------------------------------------------------
     def _step(self, n: int) -> int:
-        """Network + decode/NMS into gather slot s, then (world > 1) the all-gather on the side stream.  Returns s."""
+        """Network on the current stream into head set s, decode/NMS on the decode stream into gather slot s, then
+        (world > 1) the all-gather on the side stream.  Returns s."""
         s = self._steps % SLOTS
         self._steps += 1
         compute = torch.cuda.current_stream(self.device_index)
-        compute.wait_event(self._slot_free[s])          # whoever still reads this slot (gather / D2H two steps ago)
+        if self._head_sets is None:
+            self._head_sets = [list(self.engine.head_buffers), self.engine.new_head_set()]
+        # head set s was last read by the decode of two steps ago; that decode wrote gather slot s, too
+        compute.wait_event(self._det_done[s])
+        self.engine.bind_heads(self._head_sets[s])
         heads = self.engine.run(n)
+        self._heads_ready[s].record(compute)
+        det = self._det_stream
+        det.wait_event(self._heads_ready[s])
+        det.wait_event(self._slot_free[s])          # whoever still reads this gather slot (all-gather / D2H two steps ago)
         dets, counts = self.gather.local(s)
-        self.detector.run(heads, self._img_hw[:n], dets_out=dets, counts_out=counts)
+        self.detector.run(heads, self._img_hw[:n], dets_out=dets, counts_out=counts, stream=det)
+        self._det_done[s].record(det)
         if self.world > 1:
-            self._det_done[s].record(compute)
             self._side.wait_event(self._det_done[s])
             self.gather.gather(s, stream=self._side)
             self._gather_done[s].record(self._side)
             self._slot_free[s].record(self._side)
         return s
 
-    def step_device(self, n: Optional[int] = None):
+    def step_device(self, n: Optional[int] = None, pipelined: bool = False):
         """Network + decode/NMS (+ all-gather) on the bound device input; asynchronous.  Returns the gathered
-        (dets [world*batch, C, K, 6] int32, counts [world*batch, C]) device views; with world > 1 they are complete once
-        the current stream has passed ``wait_gathered()`` (the collective runs on a side stream)."""
+        (dets [world*batch, C, K, 6] int32, counts [world*batch, C]) device views.  ``pipelined=False``: the current stream
+        waits for them (use them like any other result of the stream).  ``pipelined=True``: the current stream does NOT wait,
+        so the next step's convolutions overlap this step's decode; the views are complete once the stream has passed
+        ``wait_gathered()`` (or after a device synchronise), and stay valid for one more ``step_device``."""
         s = self._step(self.batch if n is None else n)
         self._last_slot = s
+        if not pipelined:
+            self.wait_gathered()
         return self.gather.views(s)
 
     def wait_gathered(self) -> None:
-        """Makes the current stream wait for the all-gather of the latest ``step_device``."""
-        if self.world > 1:
-            torch.cuda.current_stream(self.device_index).wait_event(self._gather_done[self._last_slot])
+        """Makes the current stream wait for the decode (and all-gather) of the latest ``step_device``."""
+        ev = self._gather_done[self._last_slot] if self.world > 1 else self._det_done[self._last_slot]
+        torch.cuda.current_stream(self.device_index).wait_event(ev)
 
     # -- host API ---------------------------------------------------------------------------------------------------
     def _input_slots(self, u8: bool) -> List[torch.Tensor]:
@@ -128,8 +148,8 @@ class DetectionPipeline:
         self.engine.bind_input(buf)
         s = self._step(n)
         self._in_free[slot].record(compute)
-        # D2H of the gathered blocks: behind the all-gather on the side stream (world > 1), else on the compute stream
-        st = self._side if self.world > 1 else compute
+        # D2H of the gathered blocks: behind the all-gather on the side stream (world > 1), else behind the decode
+        st = self._side if self.world > 1 else self._det_stream
         with torch.cuda.stream(st):
             self._host[s].copy_(self.gather.bufs[s], non_blocking=True)
             self._d2h_done[s].record(st)

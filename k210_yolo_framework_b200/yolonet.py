@@ -200,6 +200,23 @@ class YoloEngine:
             check(lib.k2y_net_bind_input(self._h, buf.data_ptr()))
         self._ext_input = buf  # keep it alive
 
+    def bind_heads(self, heads: List[torch.Tensor]) -> None:
+        """Points the head outputs at another set of CUDA float32 buffers ``[max_batch, h, w, c]`` (one CUDA graph is kept per
+        set): with two sets, decode/NMS of batch i on another stream can overlap the convolutions of batch i+1."""
+        self._bind()
+        if len(heads) != len(self.out_shapes) or any(
+                (not t.is_cuda) or t.dtype != torch.float32 or (not t.is_contiguous()) or tuple(t.shape) != (self.max_batch,) + tuple(sh)
+                for t, sh in zip(heads, self.out_shapes)):
+            raise ValueError(f"expected contiguous CUDA float32 heads of shapes {[(self.max_batch,) + tuple(sh) for sh in self.out_shapes]}")
+        ptrs = (ctypes.c_void_p * len(heads))(*[t.data_ptr() for t in heads])
+        check(lib.k2y_net_bind_heads(self._h, ptrs, len(heads)))
+        self._heads = list(heads)
+
+    def new_head_set(self) -> List[torch.Tensor]:
+        """A second set of head buffers, shaped like the engine's own."""
+        self._bind()
+        return [torch.empty_like(t) for t in self._heads]
+
     def unbind_input(self) -> None:
         """Back to the engine's own float32 input buffer."""
         if getattr(self, "_ext_input", None) is not None:

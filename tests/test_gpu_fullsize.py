@@ -55,3 +55,34 @@ def test_bench_workload_parity(cfg_id, batch, n_forward):
         assert float(np.abs(gs.astype(np.float64) - rs).max()) < 1e-3, f"cfg{cfg_id} image {b}: confidence error"
         err = np.abs(gb / norm - rb / norm) / np.maximum(1.0, np.abs(rb / norm))
         assert float(err.max()) < 1e-3, f"cfg{cfg_id} image {b}: normalised box error {float(err.max()):.2e}"
+
+
+def test_pipelined_steps_equal_serial_steps():
+    """step_device(pipelined=True): the decode/NMS of step i (own stream, head set i % 2) overlaps the convolutions of step
+    i+1; its records are read only AFTER step i+1 has been issued, and must equal those of the same batch run alone."""
+    cfg = dict(wl.CONFIGS[2])
+    B, hw = cfg["batch"], cfg["in_hw"]
+    pipe = DetectionPipeline(cfg["model"], hw, wl.anchors(cfg), cfg["classes"], cfg["alpha"], B, wl.OBJ_THRESH, wl.IOU_THRESH,
+                             wl.MAX_PER_CLASS)
+    pipe.engine.set_weights(wl.bench_weights(cfg, pipe.engine.expected_variables()))
+    xs = [torch.from_numpy(wl.synthetic_batch(cfg, 4000 + j, B)).cuda() for j in range(5)]
+    serial = []
+    for x in xs:
+        pipe.engine.bind_input(x)
+        d, c = pipe.step_device()           # current stream waits for the decode
+        serial.append((d.clone(), c.clone()))
+    torch.cuda.synchronize()
+    for rep in range(2):                    # second pass: every (input, head set) graph already captured, launches back to back
+        got, prev = [], None
+        for x in xs + [xs[0]]:
+            pipe.engine.bind_input(x)
+            views = pipe.step_device(pipelined=True)
+            if prev is not None:
+                pipe.wait_gathered()        # decode stream is in order: step i is complete once step i+1's decode is
+                got.append((prev[0].clone(), prev[1].clone()))
+            prev = views
+        torch.cuda.synchronize()
+        for j, ((d, c), (sd, sc)) in enumerate(zip(got, serial)):
+            assert torch.equal(c, sc), f"pass {rep} step {j}: counts differ"
+            rec, ref = DetectionPipeline.records(d, c), DetectionPipeline.records(sd, sc)
+            assert rec == ref, f"pass {rep} step {j}: records differ"
