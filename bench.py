@@ -249,7 +249,7 @@ def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
     from k210_yolo_framework_b200 import _lib
-    from k210_yolo_framework_b200.pipeline import DetectionPipeline
+    from k210_yolo_framework_b200.pipeline import LanedPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,10 +265,13 @@ def run_ours(args, cfg):
                   "tc_bf16x3": _lib.MATH_TC_BF16X3}
     B, (H, W) = cfg["batch"], cfg["in_hw"]
 
-    pipe = DetectionPipeline(cfg["model"], cfg["in_hw"], wl.anchors(cfg), cfg["classes"], cfg["alpha"], B, wl.OBJ_THRESH,
-                             wl.IOU_THRESH, wl.MAX_PER_CLASS, device=local, world=world, rank=rank)
-    pipe.engine.set_weights(wl.bench_weights(cfg, pipe.engine.expected_variables()))
-    pipe.engine.set_math(math_modes[args.math])
+    # `lanes` batches in flight, each on its own engine + streams (consecutive batches are independent: the early layers of one
+    # run beside the small-grid late layers of the other); `pipe` = lane 0, used for every single-batch measurement below
+    lp = LanedPipeline(args.lanes, cfg["model"], cfg["in_hw"], wl.anchors(cfg), cfg["classes"], cfg["alpha"], B, wl.OBJ_THRESH,
+                       wl.IOU_THRESH, wl.MAX_PER_CLASS, device=local, world=world, rank=rank)
+    pipe = lp.lanes[0]
+    lp.set_weights(wl.bench_weights(cfg, pipe.engine.expected_variables()))
+    lp.set_math(math_modes[args.math])
     # distinct device-resident input batches, together larger than L2: a step never finds its input in L2
     in_bytes = B * H * W * 3 * 4
     n_in = max(2, -(-int(1.3 * L2_BYTES) // in_bytes))
@@ -285,30 +288,31 @@ def run_ours(args, cfg):
         barrier()
         e0.record(stream)
         for i in range(steps):
-            pipe.engine.bind_input(xs[i % n_in])
-            pipe.step_device(pipelined=True)   # decode/NMS of step i (own stream) overlaps the first layers of step i+1
-        pipe.wait_gathered()            # the last step's decode (and all-gather) belongs to the window
+            lp.bind_input(xs[i % n_in])
+            lp.step_device()            # next lane; decode/NMS of a step (own stream) overlaps whatever runs next
+        lp.wait_all()                   # every lane's last decode (and all-gather) belongs to the window
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1)
 
     # ---- device-resident timing -------------------------------------------------------------
     def capture_all():
-        """One CUDA graph per (input buffer, head set) — steps alternate between two head sets — captured outside warm-up and
-        timing: every input once, one extra step to flip the pairing when the inputs are even in number, every input again."""
-        for j in range(n_in):
-            pipe.engine.bind_input(xs[j])
-            pipe.step_device(pipelined=True)
-        if n_in % 2 == 0:
-            pipe.step_device(pipelined=True)
-        for j in range(n_in):
-            pipe.engine.bind_input(xs[j])
-            pipe.step_device(pipelined=True)
+        """One CUDA graph per (lane, input buffer, head set) — a lane alternates between two head sets — captured outside
+        warm-up and timing: per lane every input once, one extra step to flip the pairing when the inputs are even in number,
+        every input again."""
+        for ln in lp.lanes:
+            for rep in range(2):
+                for j in range(n_in):
+                    ln.engine.bind_input(xs[j])
+                    ln.step_device(pipelined=True)
+                if rep == 0 and n_in % 2 == 0:
+                    ln.step_device(pipelined=True)
+        torch.cuda.synchronize()
 
     capture_all()
     for i in range(args.warmup):
-        pipe.engine.bind_input(xs[i % n_in])
-        pipe.step_device(pipelined=True)
+        lp.bind_input(xs[i % n_in])
+        lp.step_device()
     barrier()
     if args.profile_step:
         # `ncu --profile-from-start off ... bench.py --profile-step`: exactly ONE step between cudaProfilerStart/Stop, cold input
@@ -335,17 +339,23 @@ def run_ours(args, cfg):
     # letterboxed RGB.  The normalisation runs on the GPU (fused into the first conv).
     n_host = max(3, -(-int(1.3 * L2_BYTES) // (in_bytes // 4)))
     hosts = [torch.from_numpy(wl.synthetic_batch_u8(cfg, 2000 + 64 * rank + j)).pin_memory() for j in range(n_host)]
-    for j in range(max(4, n_host)):     # warm-up touches every pinned batch once: the first DMA out of a buffer is slower than the rest
-        pipe.collect(pipe.submit(hosts[j % n_host]))
-    barrier()
+    from collections import deque
+
+    def stream_host(batches, steps):
+        """submit/collect with as many batches in flight as the lanes allow; returns the last batch's host records"""
+        q, out = deque(), None
+        for i in range(steps):
+            q.append(lp.submit(batches[i % len(batches)]))
+            if len(q) >= lp.in_flight_limit():
+                out = lp.collect(q.popleft())
+        while q:
+            out = lp.collect(q.popleft())
+        return out
+
+    stream_host(hosts, max(4, n_host) + 2 * lp.in_flight_limit())   # warm-up touches every pinned batch once (the first DMA out of
+    barrier()                                                        # a buffer is slower) and every (lane, slot, head set) graph
     t0 = time.perf_counter()
-    prev = None
-    for i in range(args.steps):
-        tk = pipe.submit(hosts[i % n_host])
-        if prev is not None:
-            pipe.collect(prev)
-        prev = tk
-    hd, hc = pipe.collect(prev)
+    hd, hc = stream_host(hosts, args.steps)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
@@ -361,18 +371,11 @@ def run_ours(args, cfg):
     e2e_sync_ms = 1000.0 * t_sync / 5
     # same streaming loop fed with float32 host batches (4x the PCIe bytes)
     hosts_f = [torch.from_numpy(wl.synthetic_batch(cfg, 3000 + 16 * rank + j)).pin_memory() for j in range(max(2, min(n_in, 4)))]
-    for j in range(3):
-        pipe.collect(pipe.submit(hosts_f[j % len(hosts_f)]))
+    stream_host(hosts_f, 3 * lp.in_flight_limit())
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    prev = None
     f_steps = max(5, args.steps // 2)
-    for i in range(f_steps):
-        tk = pipe.submit(hosts_f[i % len(hosts_f)])
-        if prev is not None:
-            pipe.collect(prev)
-        prev = tk
-    pipe.collect(prev)
+    stream_host(hosts_f, f_steps)
     torch.cuda.synchronize()
     e2e_f32_ms = 1000.0 * (time.perf_counter() - t2) / f_steps
     clocks = sampler.stop() if rank == 0 else None
@@ -397,12 +400,12 @@ def run_ours(args, cfg):
     # (b) the precision-matched arithmetic (3xTF32: tf32 tensor cores, hi/lo split, ~fp32 products) beside the default
     matched = None
     if args.math != "tc_3xtf32":
-        pipe.engine.set_math(math_modes["tc_3xtf32"])
+        lp.set_math(math_modes["tc_3xtf32"])
         capture_all()
         m_steps = min(args.steps, 20)
         m_ms = timed_steps(m_steps)
         matched = {"math": "tc_3xtf32", "steps": m_steps, "ms": m_ms}
-        pipe.engine.set_math(math_modes[args.math])
+        lp.set_math(math_modes[args.math])
         capture_all()
         barrier()
 
@@ -486,13 +489,15 @@ def run_ours(args, cfg):
             "arm": {"math": args.math,
                     "parallelism": f"image-shard x{world}" + (", one ncclAllGather per step on a side stream" if world > 1 else ""),
                     "l2": f"{n_in} distinct device-resident input batches in rotation ({n_in * in_bytes >> 20} MiB > 126 MiB L2), no flush inside the window",
-                    "streams": "network graph on the launching stream; decode + NMS of step i on a second stream, overlapping the "
-                               "first layers of step i+1 (two head-buffer sets); the last step's decode is inside the timed window",
+                    "lanes": args.lanes,
+                    "streams": f"{args.lanes} batches in flight, one lane (engine + arena + streams) each, fed round-robin: a lane runs "
+                               "its network graph on its compute stream and decode + NMS on a second stream (two head-buffer sets); "
+                               "every lane's last decode is inside the timed window",
                     "detections_per_step": n_found},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "images/sec",
                     "h2d_bytes_per_step": int(hosts[0].numel()), "d2h_bytes_per_step": d2h_bytes,
-                    "api": "DetectionPipeline.submit/collect (pinned host uint8 NHWC letterboxed RGB in, detection records out; "
-                           "img/max(img) on the GPU; H2D of step i+1 overlaps step i, no staging copy)",
+                    "api": "LanedPipeline.submit/collect (pinned host uint8 NHWC letterboxed RGB in, detection records out; "
+                           "img/max(img) on the GPU; H2D of later batches overlaps the running ones, no staging copy)",
                     "inputs": f"{n_host} distinct pinned host batches in rotation",
                     "single_call_ms": e2e_sync_ms,
                     "f32_host_input": {"value": world * B / (e2e_f32_ms * 1e-3), "h2d_bytes_per_step": in_bytes}},
@@ -528,6 +533,8 @@ def main():
     ap.add_argument("--config", type=int, choices=sorted(wl.CONFIGS), default=2,
                     help="BASELINE.json config: 2 yolo_mobilev1-0.75 (default, the headline), 3 tiny_yolo 416, 4 yolo_mobilev2, 5 Darknet-53 608")
     ap.add_argument("--math", choices=["fp32_simt", "tc_3xtf32", "tc_tf32", "tc_bf16x3"], default=os.environ.get("K2Y_BENCH_MATH", "tc_bf16x3"))
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("K2Y_BENCH_LANES", "2")),
+                    help="batches in flight on one GPU (each lane = engine + activation arena + streams); 1 = strictly one batch at a time")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs (profiling runs)")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run exactly one step between cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -32,7 +32,7 @@ SLOTS = 2
 class DetectionPipeline:
     def __init__(self, model_def: str, image_size: Sequence[int], anchors: np.ndarray, class_num: int, alpha: float,
                  batch: int, obj_thresh: float = 0.7, iou_thresh: float = 0.3, max_per_class: int = 30,
-                 device: Optional[int] = None, world: int = 1, rank: int = 0):
+                 device: Optional[int] = None, world: int = 1, rank: int = 0, comm=None):
         self.batch, self.world, self.rank = int(batch), int(world), int(rank)
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         builder = getattr(yolonet, model_def)
@@ -44,7 +44,7 @@ class DetectionPipeline:
                                       max_batch=batch, device=self.device_index)
         dev = torch.device("cuda", self.device_index)
         self.gather = DetectionGather(batch, class_num, max_per_class, dev, world=self.world, rank=self.rank, words=DET_WORDS,
-                                      slots=SLOTS)
+                                      slots=SLOTS, comm=comm)
         self._img_hw = torch.tensor([[image_size[0], image_size[1]]] * batch, dtype=torch.float32, device=dev)
         self._side = torch.cuda.Stream(device=dev)          # all-gather + D2H of gathered blocks
         self._det_stream = torch.cuda.Stream(device=dev, priority=-1)   # decode + NMS (its CTAs go first when SM slots free up)
@@ -168,3 +168,79 @@ class DetectionPipeline:
     @staticmethod
     def records(dets: torch.Tensor, counts: torch.Tensor) -> List[list]:
         return KerasDetector.to_host(dets, counts)
+
+
+class LanedPipeline:
+    """Several batches in flight: ``lanes`` DetectionPipelines (own engine + activation arena, own streams, one shared NCCL
+    communicator) fed round-robin, each on its own compute stream.  Consecutive batches are independent, so batch i+1's
+    bandwidth-bound early layers run beside batch i's small-grid late layers (which leave most SMs idle) — the multi-stream
+    serving form of the same per-batch work; every batch still goes through the same kernels with the same batch size.
+
+    ``bind_input(x)`` / ``step_device()`` / ``wait_all()`` for device-resident inputs, ``submit`` / ``collect`` for pinned
+    host batches (tickets carry the lane)."""
+
+    def __init__(self, lanes: int, *args, **kw):
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        first = DetectionPipeline(*args, **kw)
+        self.lanes: List[DetectionPipeline] = [first] + [DetectionPipeline(*args, comm=first.gather.comm, **kw) for _ in range(lanes - 1)]
+        self.batch, self.world, self.rank, self.device_index = first.batch, first.world, first.rank, first.device_index
+        dev = torch.device("cuda", self.device_index)
+        self._streams = [torch.cuda.Stream(device=dev) for _ in self.lanes]
+        self._fork = torch.cuda.Event()
+        self._next = 0          # next lane for step_device
+        self._next_host = 0     # next lane for submit
+        self._ran = [False] * lanes
+
+    def set_weights(self, weights) -> None:
+        for ln in self.lanes:
+            ln.engine.set_weights(weights)
+
+    def set_math(self, mode) -> None:
+        for ln in self.lanes:
+            ln.engine.set_math(mode)
+
+    def set_image_shapes(self, image_hw) -> None:
+        for ln in self.lanes:
+            ln.set_image_shapes(image_hw)
+
+    def bind_input(self, x: torch.Tensor) -> None:
+        """Device input of the NEXT ``step_device`` (float32 or uint8 [batch,H,W,3])."""
+        self.lanes[self._next % len(self.lanes)].engine.bind_input(x)
+
+    def step_device(self, n: Optional[int] = None):
+        """One batch on the next lane (asynchronous, on the lane's stream, ordered after the caller's current stream).  The
+        returned views are complete after ``wait_all()`` and stay valid until that lane has run two more batches."""
+        k = self._next % len(self.lanes)
+        self._next += 1
+        cur = torch.cuda.current_stream(self.device_index)
+        self._fork.record(cur)
+        st = self._streams[k]
+        st.wait_event(self._fork)
+        with torch.cuda.stream(st):
+            views = self.lanes[k].step_device(n, pipelined=True)
+        self._ran[k] = True
+        return views
+
+    def wait_all(self) -> None:
+        """Makes the current stream wait for everything issued with ``step_device`` so far (decode / all-gather of every lane)."""
+        for k, ln in enumerate(self.lanes):
+            if self._ran[k]:
+                ln.wait_gathered()
+
+    def submit(self, x_host: torch.Tensor):
+        k = self._next_host % len(self.lanes)
+        self._next_host += 1
+        with torch.cuda.stream(self._streams[k]):
+            return (k, self.lanes[k].submit(x_host))
+
+    def collect(self, ticket):
+        k, t = ticket
+        return self.lanes[k].collect(t)
+
+    def in_flight_limit(self) -> int:
+        """Batches that may be submitted before the oldest must be collected."""
+        return SLOTS * len(self.lanes)
+
+    def launches_per_step(self) -> int:
+        return self.lanes[0].launches_per_step()

@@ -86,3 +86,51 @@ def test_pipelined_steps_equal_serial_steps():
             assert torch.equal(c, sc), f"pass {rep} step {j}: counts differ"
             rec, ref = DetectionPipeline.records(d, c), DetectionPipeline.records(sd, sc)
             assert rec == ref, f"pass {rep} step {j}: records differ"
+
+
+def test_laned_pipeline_equals_serial_steps():
+    """LanedPipeline: two batches in flight on two engines / stream sets; device-resident and host-streaming forms both
+    return, batch for batch, the records of the same batch run alone."""
+    from collections import deque
+    from k210_yolo_framework_b200.pipeline import LanedPipeline
+    cfg = dict(wl.CONFIGS[2])
+    B, hw = cfg["batch"], cfg["in_hw"]
+    lp = LanedPipeline(2, cfg["model"], hw, wl.anchors(cfg), cfg["classes"], cfg["alpha"], B, wl.OBJ_THRESH, wl.IOU_THRESH,
+                       wl.MAX_PER_CLASS)
+    lp.set_weights(wl.bench_weights(cfg, lp.lanes[0].engine.expected_variables()))
+    xs_host = [torch.from_numpy(wl.synthetic_batch(cfg, 5000 + j, B)).pin_memory() for j in range(6)]
+    xs = [x.cuda() for x in xs_host]
+    serial = []
+    for x in xs:
+        lp.lanes[0].engine.bind_input(x)
+        d, c = lp.lanes[0].step_device()
+        serial.append(DetectionPipeline.records(d.clone(), c.clone()))
+    torch.cuda.synchronize()
+    # device-resident: a lane's views stay valid until it has run two more batches -> read batch i after issuing batch i+1
+    for rep in range(2):
+        got, pending = [], deque()
+        for x in xs:
+            lp.bind_input(x)
+            pending.append(lp.step_device())
+            if len(pending) == 2:
+                lp.wait_all()
+                d, c = pending.popleft()
+                got.append(DetectionPipeline.records(d.clone(), c.clone()))
+        lp.wait_all()
+        while pending:
+            d, c = pending.popleft()
+            got.append(DetectionPipeline.records(d.clone(), c.clone()))
+        torch.cuda.synchronize()
+        assert got == serial, f"device-resident pass {rep}"
+    # host streaming
+    for rep in range(2):
+        got, q = [], deque()
+        for x in xs_host:
+            q.append(lp.submit(x))
+            if len(q) >= lp.in_flight_limit():
+                d, c = lp.collect(q.popleft())
+                got.append(DetectionPipeline.records(d.clone(), c.clone()))
+        while q:
+            d, c = lp.collect(q.popleft())
+            got.append(DetectionPipeline.records(d.clone(), c.clone()))
+        assert got == serial, f"host streaming pass {rep}"
