@@ -915,12 +915,6 @@ int tc_init() {
                                         (int)prop.sharedMemPerBlockOptin));
     if (g_num_sms == 0) {
         g_max_smem = prop.sharedMemPerBlockOptin;
-        // experiment knob: cap the dynamic shared memory of the tensor-core conv (e.g. 112 -> two CTAs fit one SM, which matters
-        // when two batches are in flight on separate streams); the planner then picks fewer stages / narrower tiles
-        if (const char *kb = getenv("K2Y_TC_SMEM_KB")) {
-            const size_t cap = (size_t)atoi(kb) * 1024;
-            if (cap >= 48 * 1024 && cap < g_max_smem) g_max_smem = cap;
-        }
         g_num_sms = prop.multiProcessorCount;
     }
     K2Y_CUDA_CHECK(cudaMalloc(&ds.ones, ID_LEN * sizeof(float)));
