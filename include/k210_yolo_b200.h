@@ -94,6 +94,11 @@ int k2y_net_bind_u8(k2y_net *net, const unsigned char *x_u8_dev, int32_t *img_ma
  * graph is kept per (batch, input buffer), so alternating between two input buffers (H2D of batch i+1 while batch i runs)
  * costs nothing after the first use of each.  k2y_net_bind_u8 behaves the same way for the uint8 input. */
 int k2y_net_bind_input(k2y_net *net, const float *x_dev);
+/* SM budget of this net's persistent tensor-core kernels (tile planner + grid sizes); 0 (default) = the whole device.  Nets
+ * that run concurrently on one GPU (several batches in flight on separate streams) should each take their share — 148 / 2 on
+ * a B200 with two in flight — so that their one-CTA-per-SM grids run side by side instead of queueing behind each other.
+ * Results do not depend on it bit for bit only where the tile shapes stay the same; they stay within the conv tolerance. */
+int k2y_net_set_sm_limit(k2y_net *net, int sms);
 /* Re-points the head outputs at another set of device buffers (same shapes as in k2y_net_bind).  One CUDA graph is kept per
  * (batch, input buffer, first head buffer): alternating between two head sets lets the decode/NMS of batch i (reading set A on
  * another stream) overlap the convolutions of batch i+1 (writing set B) at no re-capture cost. */

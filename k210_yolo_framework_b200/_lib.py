@@ -70,6 +70,7 @@ _SIGNATURES = {
     "k2y_net_bind_u8": (c_int, [c_void_p, c_void_p, c_void_p]),
     "k2y_net_bind_input": (c_int, [c_void_p, c_void_p]),
     "k2y_net_bind_heads": (c_int, [c_void_p, POINTER(c_void_p), c_int]),
+    "k2y_net_set_sm_limit": (c_int, [c_void_p, c_int]),
     "k2y_net_run": (c_int, [c_void_p, c_int, c_void_p]),
     "k2y_net_predict_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_void_p), c_void_p]),
     "k2y_net_launches_per_run": (c_int, [c_void_p, POINTER(c_int)]),

@@ -50,6 +50,10 @@ struct ConvArgs {
     // per-device default of the single-layer test hook
     float *tc_scratch = nullptr;
     size_t tc_scratch_bytes = 0;
+    // SM budget of the persistent tensor-core kernels (tile planner + grid size); 0 = the whole device.  A net that shares the
+    // GPU with other nets in flight (LanedPipeline) plans for its share, so that the lanes' kernels run side by side instead of
+    // queueing behind each other's one-CTA-per-SM grids
+    int sm_limit = 0;
 };
 
 struct DwArgs {

@@ -602,7 +602,9 @@ bool plan_dwpw(const DwArgs &dw, const ConvArgs &pw, int dev, DwPwPlan *out) {
     off += (uint32_t)sizeof(DpBarriers);
     out->smem = (size_t)off + 1024;  // + alignment slack
     if (out->smem > g_dp_smem[dev]) return false;
-    out->grid = p.num_tiles < g_dp_sms[dev] ? p.num_tiles : g_dp_sms[dev];
+    int sms = g_dp_sms[dev];
+    if (pw.sm_limit > 0 && pw.sm_limit < sms) sms = pw.sm_limit < 8 ? 8 : pw.sm_limit;   // the net's SM budget (ConvArgs::sm_limit)
+    out->grid = p.num_tiles < sms ? p.num_tiles : sms;
     return true;
 }
 

@@ -832,11 +832,18 @@ int pick_cluster(int M, int nkb) {
     return ((M + BM - 1) / BM >= 2 && nkb >= 4) ? 2 : 1;
 }
 
-void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int cluster, size_t scratch_limit, int *bn_out, int *splits_out) {
+// SMs a conv may plan for: the device's, or the caller's budget (even, >= 8) when it asks for less
+int budget_sms(int sm_limit) {
+    const int all = g_num_sms > 0 ? g_num_sms : 148;
+    if (sm_limit <= 0 || sm_limit >= all) return all;
+    return (sm_limit < 8 ? 8 : sm_limit) & ~1;
+}
+
+void pick_tile(int M, int N, int nkb, bool three_x, bool bf16, bool gather, int cluster, size_t scratch_limit, int sms, int *bn_out,
+               int *splits_out) {
     if (scratch_limit == 0) scratch_limit = DEFAULT_SCRATCH_BYTES;
     const int n16 = (N + 15) / 16 * 16;
     const int m_tiles = (M + BM - 1) / BM;
-    const int sms = g_num_sms > 0 ? g_num_sms : 148;
     const char *force = getenv("K2Y_TC_SPLITK");
     int best = 16, best_s = 1;
     double best_cost = 1e30;
@@ -1084,8 +1091,8 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.a_boxes = p.bf16 ? 2 : 1;
     p.nkb = p.bf16 ? w.Kpad64 / 64 : w.Kpad / BK;
     p.cluster = pick_cluster(p.M, p.nkb);
-    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a) || dw, p.cluster, a.tc_scratch ? a.tc_scratch_bytes : 0, &p.BN,
-              &p.k_splits);
+    pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a) || dw, p.cluster, a.tc_scratch ? a.tc_scratch_bytes : 0,
+              budget_sms(a.sm_limit), &p.BN, &p.k_splits);
     p.n_tiles = (w.Npad + p.BN - 1) / p.BN;
     p.m_tiles = (p.M + BM - 1) / BM;
     p.kb_per_split = (p.nkb + p.k_splits - 1) / p.k_splits;
@@ -1143,7 +1150,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     }
 
     const int tiles = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_tiles * p.k_splits;  // work items per cluster
-    const int max_clusters = g_num_sms / p.cluster;
+    const int max_clusters = budget_sms(a.sm_limit) / p.cluster;
     const int grid = (tiles < max_clusters ? tiles : max_clusters) * p.cluster;
     p.trace = nullptr;
     p.dbg = getenv("K2Y_TC_DBG") ? atoi(getenv("K2Y_TC_DBG")) : 0;
@@ -1223,7 +1230,8 @@ int tc_launch_count(const ConvArgs &a, const TcWeights &w, int math_mode) {
     const int mode = effective_mode(a, math_mode);
     const bool bf = mode == K2Y_MATH_TC_BF16X3;
     const int M = a.B * a.OH * a.OW, nkb = bf ? w.Kpad64 / 64 : w.Kpad / BK;
-    pick_tile(M, a.N, nkb, mode != K2Y_MATH_TC_TF32, bf, !is_plain_1x1(a), pick_cluster(M, nkb), a.tc_scratch ? a.tc_scratch_bytes : 0, &bn, &splits);
+    pick_tile(M, a.N, nkb, mode != K2Y_MATH_TC_TF32, bf, !is_plain_1x1(a), pick_cluster(M, nkb), a.tc_scratch ? a.tc_scratch_bytes : 0,
+              budget_sms(a.sm_limit), &bn, &splits);
     return splits > 1 ? 2 : 1;
 }
 
@@ -1258,7 +1266,7 @@ extern "C" int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *b
     const bool bf = mode == K2Y_MATH_TC_BF16X3, three_x = mode != K2Y_MATH_TC_TF32;
     const int nkb = bf ? (K + 63) / 64 : (K + BK - 1) / BK;
     *cluster = pick_cluster(M, nkb);
-    pick_tile(M, N, nkb, three_x, bf, gather, *cluster, 0, bn, k_splits);
+    pick_tile(M, N, nkb, three_x, bf, gather, *cluster, 0, budget_sms(0), bn, k_splits);
     const size_t stage_bytes = (size_t)A_TILE_BYTES * (bf ? 2 : 1) + (size_t)(*bn) * 128 * (three_x ? 2 : 1);
     int st = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage_bytes);
     if (st > MAX_STAGES) st = MAX_STAGES;

@@ -98,6 +98,7 @@ struct k2y_net {
     std::map<std::tuple<int, const void *, const void *, const void *, const void *>, cudaGraphExec_t> graphs;  // (batch, x, x_u8, img_max, head 0)
     int last_batch = 0;
     int launches = 0;  // kernels issued by the last issue_layers() pass
+    int sm_limit = 0;              // SM budget of the persistent tensor-core kernels (0 = whole device), k2y_net_set_sm_limit
     float *tc_scratch = nullptr;   // this net's split-K partials (never shared with another net / stream)
     size_t tc_scratch_bytes = 0;
 
@@ -459,6 +460,7 @@ int issue_layers(k2y_net *n, int batch, cudaStream_t st, cudaEvent_t *ev = nullp
         a.alpha = L.alpha;
         a.tc_scratch = n->tc_scratch;
         a.tc_scratch_bytes = n->tc_scratch_bytes;
+        a.sm_limit = n->sm_limit;
         return a;
     };
     int dw_ordinal = 0;
@@ -974,6 +976,17 @@ extern "C" int k2y_net_bind_input(k2y_net *net, const float *x_dev) {
         return K2Y_ERR_INVALID;
     }
     net->x_dev = x_dev;
+    return K2Y_OK;
+}
+
+extern "C" int k2y_net_set_sm_limit(k2y_net *net, int sms) {
+    if (check_net(net, "k2y_net_set_sm_limit")) return K2Y_ERR_INVALID;
+    if (sms < 0) {
+        set_error("k2y_net_set_sm_limit: sms must be >= 0 (0 = whole device)");
+        return K2Y_ERR_INVALID;
+    }
+    if (sms != net->sm_limit) drop_graphs(net);
+    net->sm_limit = sms;
     return K2Y_OK;
 }
 

@@ -173,13 +173,14 @@ class DetectionPipeline:
 class LanedPipeline:
     """Several batches in flight: ``lanes`` DetectionPipelines (own engine + activation arena, own streams, one shared NCCL
     communicator) fed round-robin, each on its own compute stream.  Consecutive batches are independent, so batch i+1's
-    bandwidth-bound early layers run beside batch i's small-grid late layers (which leave most SMs idle) — the multi-stream
-    serving form of the same per-batch work; every batch still goes through the same kernels with the same batch size.
+    bandwidth-bound early layers run beside batch i's small-grid late layers — the multi-stream serving form of the same
+    per-batch work; every batch still goes through the same kernels with the same batch size.  With ``sm_split`` (default) every
+    lane sizes its persistent tensor-core grids for 1/lanes of the SMs, so the lanes' kernels share the GPU side by side.
 
     ``bind_input(x)`` / ``step_device()`` / ``wait_all()`` for device-resident inputs, ``submit`` / ``collect`` for pinned
     host batches (tickets carry the lane)."""
 
-    def __init__(self, lanes: int, *args, **kw):
+    def __init__(self, lanes: int, *args, sm_split: bool = True, **kw):
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
         first = DetectionPipeline(*args, **kw)
@@ -191,6 +192,13 @@ class LanedPipeline:
         self._next = 0          # next lane for step_device
         self._next_host = 0     # next lane for submit
         self._ran = [False] * lanes
+        # each lane plans its persistent tensor-core kernels for 1/lanes of the SMs: two lanes' one-CTA-per-SM grids then run
+        # side by side (measured on cfg 2, two lanes: 69.3 k -> 77 k images/s; see profiles/r02_lanes.md)
+        self.sm_limit = 0
+        if sm_split and lanes > 1:
+            self.sm_limit = torch.cuda.get_device_properties(dev).multi_processor_count // lanes
+            for ln in self.lanes:
+                ln.engine.set_sm_limit(self.sm_limit)
 
     def set_weights(self, weights) -> None:
         for ln in self.lanes:

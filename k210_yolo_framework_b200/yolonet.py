@@ -200,6 +200,10 @@ class YoloEngine:
             check(lib.k2y_net_bind_input(self._h, buf.data_ptr()))
         self._ext_input = buf  # keep it alive
 
+    def set_sm_limit(self, sms: int) -> None:
+        """SM budget of this net's persistent tensor-core kernels (0 = whole device); see k2y_net_set_sm_limit."""
+        check(lib.k2y_net_set_sm_limit(self._h, int(sms)))
+
     def bind_heads(self, heads: List[torch.Tensor]) -> None:
         """Points the head outputs at another set of CUDA float32 buffers ``[max_batch, h, w, c]`` (one CUDA graph is kept per
         set): with two sets, decode/NMS of batch i on another stream can overlap the convolutions of batch i+1."""
