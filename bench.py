@@ -333,9 +333,15 @@ def run_ours(args, cfg):
             emit(json.dumps({"profile_step": True, "config": workload_config(cfg, world), "schedule": names,
                              "launches_per_step": pipe.launches_per_step()}))
         return
+    # the clock sampler (one `nvidia-smi -lms 100` process for the whole measurement) is started BEFORE a second warm-up round:
+    # its start-up (NVML initialisation) stalls kernel launches for a few milliseconds, which must not land in the timed window
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    for i in range(args.warmup):
+        lp.bind_input(xs[i % n_in])
+        lp.step_device()
     dev_ms = timed_steps(args.steps)
 
     # ---- end to end: pinned host input -> H2D -> step -> D2H records ----------------------------
@@ -360,10 +366,14 @@ def run_ours(args, cfg):
 
     stream_host(hosts, max(4, n_host) + 2 * lp.in_flight_limit())   # warm-up touches every pinned batch once (the first DMA out of
     barrier()                                                        # a buffer is slower) and every (lane, slot, head set) graph
-    t0 = time.perf_counter()
-    hd, hc = stream_host(hosts, args.steps)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
+    e2e_windows = []
+    for _ in range(3):                  # three windows of K steps each; the median is reported (host-timed, ~20 ms windows)
+        barrier()
+        t0 = time.perf_counter()
+        hd, hc = stream_host(hosts, args.steps)
+        torch.cuda.synchronize()
+        e2e_windows.append(time.perf_counter() - t0)
+    t_e2e = sorted(e2e_windows)[1]
     barrier()
     d2h_bytes = int(pipe.gather.bufs[0].numel() * 4)
     n_found = int(hc.sum())
@@ -513,6 +523,7 @@ def run_ours(args, cfg):
                     "api": "LanedPipeline.submit/collect (pinned host uint8 NHWC letterboxed RGB in, detection records out; "
                            "img/max(img) on the GPU; H2D of later batches overlaps the running ones, no staging copy)",
                     "inputs": f"{n_host} distinct pinned host batches in rotation",
+                    "windows_ms": [round(1000.0 * w, 3) for w in e2e_windows], "reported": "median of three windows of K steps",
                     "single_call_ms": e2e_sync_ms,
                     "f32_host_input": {"value": world * B / (e2e_f32_ms * 1e-3), "h2d_bytes_per_step": in_bytes}},
             "gpu_launches": pipe.launches_per_step() * args.steps,

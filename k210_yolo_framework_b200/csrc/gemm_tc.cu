@@ -59,6 +59,7 @@ struct TcParams {
     int three_x;                    // 1 = split scheme (3 MMAs per k-step: lo*hi + hi*lo + hi*hi), 0 = single pass
     int bf16;                       // 1 = bf16x3: operands are bf16 (hi, mid) planes, 64 k per k-block; 0 = tf32, 32 k per k-block
     int a_boxes;                    // 16 KB sub-tiles of raw fp32 A per stage (k per k-block / 32)
+    int half_taps;                  // gather, tf32 k-blocks only: Cin == 16, a 32-wide k-block holds TWO taps of 16 channels (tiny_yolo's 16->32 conv)
     uint32_t tmem_cols;
     float act_slope, act_clamp;     // branch-free activation parameters
     int epi_groups;                 // 1, or 2: the idle gather warps form a second epilogue group (plain 1x1 convs)
@@ -570,7 +571,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int iy = iy0 + ky, ix = ix0 + kx;
                     const bool ok = b >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
                     unsigned long long pr = 0ull;  // 0 = zero-fill (padding / rows beyond M)
-                    if (ok) {
+                    unsigned long long pr2 = 0ull; // half_taps: the second tap of the k-block (channels 16..31 of the block)
+                    if (p.half_taps) {
+                        // k-block kb = taps 2 kb and 2 kb + 1, 16 channels (64 bytes) each; tap kh*kw (K padding) stays zero
+                        const int t0 = 2 * kb;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int tp = t0 + h;
+                            const int ky2 = tp / p.kw, kx2 = tp - ky2 * p.kw;
+                            const int iy2 = iy0 + ky2, ix2 = ix0 + kx2;
+                            const bool ok2 = b >= 0 && tp < p.kh * p.kw && iy2 >= 0 && iy2 < p.H && ix2 >= 0 && ix2 < p.W;
+                            const unsigned long long a2 =
+                                ok2 ? (unsigned long long)(p.src0 + ((size_t)(b * p.H + iy2) * p.W + ix2) * p.C0) : 0ull;
+                            if (h == 0) pr = a2;
+                            else pr2 = a2;
+                        }
+                    } else if (ok) {
                         const float *src;
                         if (ci < p.C0) {
                             if (p.up0)
@@ -597,13 +613,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     } else {
                         const int cjj = lane & 7;
+                        if (p.half_taps) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int lr = 4 * i + (lane >> 3);
-                            const unsigned long long q = __shfl_sync(0xffffffffu, pr, lr);
-                            const int row = wrow0 + lr;
-                            cp_async_16(stg_a + (uint32_t)row * 128u + (uint32_t)((cjj ^ (row & 7)) << 4),
-                                        q ? (const void *)(q + (unsigned long long)cjj * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                            for (int i = 0; i < 8; ++i) {
+                                const int lr = 4 * i + (lane >> 3);
+                                const unsigned long long q0 = __shfl_sync(0xffffffffu, pr, lr);
+                                const unsigned long long q1 = __shfl_sync(0xffffffffu, pr2, lr);
+                                const unsigned long long q = (cjj & 4) ? q1 : q0;   // chunks 0-3: first tap, 4-7: second tap
+                                const int row = wrow0 + lr;
+                                cp_async_16(stg_a + (uint32_t)row * 128u + (uint32_t)((cjj ^ (row & 7)) << 4),
+                                            q ? (const void *)(q + (unsigned long long)(cjj & 3) * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int lr = 4 * i + (lane >> 3);
+                                const unsigned long long q = __shfl_sync(0xffffffffu, pr, lr);
+                                const int row = wrow0 + lr;
+                                cp_async_16(stg_a + (uint32_t)row * 128u + (uint32_t)((cjj ^ (row & 7)) << 4),
+                                            q ? (const void *)(q + (unsigned long long)cjj * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                            }
                         }
                     }
                     cp_async_mbar_arrive_noinc(smem_u32(&bars->full_a[s]));
@@ -1001,6 +1030,10 @@ void tc_free(TcWeights &w) {
 
 // bf16x3 needs whole 64-channel k-blocks per tap in the gather path; layers that do not fit run as 3xTF32
 static bool is_plain_1x1(const ConvArgs &a);
+// 3x3 (or any kh x kw > 1) conv over ONE plain 16-channel source: k-blocks of 32 = two taps of 16 channels
+static bool is_half_taps(const ConvArgs &a) {
+    return !is_plain_1x1(a) && a.C0 == 16 && a.C1 == 0 && a.src1 == nullptr && !a.up0;
+}
 static int effective_mode(const ConvArgs &a, int math_mode) {
     if (math_mode != K2Y_MATH_TC_BF16X3) return math_mode;
     // K <= 32 fits one 32-wide tf32 k-block: half the A bytes staged and converted per tile of the 64-wide bf16 k-block
@@ -1018,9 +1051,11 @@ bool tc_supported(const ConvArgs &a, const TcWeights &w) {
     if (!w.d_hi || !get_encode()) return false;
     const int Cin = a.C0 + a.C1;
     if (is_plain_1x1(a)) return (Cin % 4) == 0 && (((uintptr_t)a.src0) & 15) == 0;  // TMA: 16-byte row pitch
-    // gather path: every k-block is one 128-byte channel run of one tap of one source
-    return (Cin % BK) == 0 && (a.C0 % BK) == 0 && (((uintptr_t)a.src0) & 15) == 0 &&
-           (a.src1 == nullptr || (((uintptr_t)a.src1) & 15) == 0);
+    // gather path: every k-block is one 128-byte channel run of one tap of one source ...
+    if ((Cin % BK) == 0 && (a.C0 % BK) == 0)
+        return (((uintptr_t)a.src0) & 15) == 0 && (a.src1 == nullptr || (((uintptr_t)a.src1) & 15) == 0);
+    // ... or two 64-byte runs of two consecutive taps (Cin == 16, one plain source; runs as 3xTF32: effective_mode)
+    return is_half_taps(a) && (((uintptr_t)a.src0) & 15) == 0;
 }
 
 // Depthwise 3x3 (+BN+act) followed by a plain 1x1 conv whose K fits one k-block: the depthwise result is produced straight
@@ -1089,6 +1124,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.bf16 = (math_mode == K2Y_MATH_TC_BF16X3) ? 1 : 0;
     p.three_x = (math_mode == K2Y_MATH_TC_TF32) ? 0 : 1;
     p.a_boxes = p.bf16 ? 2 : 1;
+    p.half_taps = (!dw && is_half_taps(a)) ? 1 : 0;   // (never bf16: effective_mode sends Cin % 64 != 0 to 3xTF32)
     p.nkb = p.bf16 ? w.Kpad64 / 64 : w.Kpad / BK;
     p.cluster = pick_cluster(p.M, p.nkb);
     pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a) || dw, p.cluster, a.tc_scratch ? a.tc_scratch_bytes : 0,

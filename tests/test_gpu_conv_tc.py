@@ -77,6 +77,8 @@ SHAPES = [
     (2, 12, 12, 64, 0, 0, 64, 3, 1, 0, 1, True),       # darknet resblock 3x3 with residual add
     (2, 6, 6, 256, 512, 1, 256, 1, 1, 0, 1, False),    # make_last_layers first 1x1 on upsample || skip concat (gather, k=1)
     (1, 13, 13, 1024, 0, 0, 256, 1, 1, 0, 1, False),   # tiny_yolo 1x1 1024->256
+    (2, 26, 30, 16, 0, 0, 32, 3, 1, 0, 1, False),      # tiny_yolo 3x3 16->32: two 16-channel taps per k-block, K = 144 padded to 160
+    (1, 17, 19, 16, 0, 0, 48, 3, 2, 2, 1, False),      # same gather form, stride 2 with pad((1,0),(1,0)), odd extents
 ]
 
 
