@@ -59,11 +59,12 @@ struct TcParams {
     int three_x;                    // 1 = split scheme (3 MMAs per k-step: lo*hi + hi*lo + hi*hi), 0 = single pass
     int bf16;                       // 1 = bf16x3: operands are bf16 (hi, mid) planes, 64 k per k-block; 0 = tf32, 32 k per k-block
     int a_boxes;                    // 16 KB sub-tiles of raw fp32 A per stage (k per k-block / 32)
-    int half_taps;                  // gather, tf32 k-blocks only: Cin == 16, a 32-wide k-block holds TWO taps of 16 channels (tiny_yolo's 16->32 conv)
+    int half_taps;                  // gather: Cin is half a k-block (16 with tf32, 32 with bf16 k-blocks), a k-block holds TWO consecutive taps
     uint32_t tmem_cols;
     float act_slope, act_clamp;     // branch-free activation parameters
     int epi_groups;                 // 1, or 2: the idle gather warps form a second epilogue group (plain 1x1 convs)
-    int tma_store;                  // 1: epilogue writes through a TMA store (N % 4 == 0, no residual)
+    int tma_store;                  // 1: epilogue writes through a TMA store (N % 4 == 0)
+    int res_tma;                    // 1: the residual (Add) operand of a TMA-store epilogue is fetched by TMA into the staging buffer
     // fused depthwise producer (gather variant, nkb == 1): A = act(BN(depthwise3x3(src0))) is computed by the gather warps
     int dw;
     const float *dw_w, *dw_scale, *dw_shift;  // [9][C0], [C0], [C0]
@@ -97,6 +98,7 @@ __device__ __forceinline__ long long gtime() {
 struct __align__(8) Barriers {
     uint64_t full_b[MAX_STAGES], full_a[MAX_STAGES], conv[MAX_STAGES], empty[MAX_STAGES];
     uint64_t tmem_full[2], tmem_empty[2];
+    uint64_t res_full[8];   // one per epilogue warp: its residual chunk (TMA load into the staging buffer) has landed
     uint32_t tmem_slot;
 };
 // dynamic smem besides the stage ring: alignment slack, barriers, epilogue staging (2 x 4 KB per epilogue warp)
@@ -153,7 +155,7 @@ template <bool GATHER, bool DWFUSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_out,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap map_res, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages] x { A_hi(raw) 16K | A_lo 16K (3x) | B_hi BN*128 | B_lo BN*128 (3x) }, then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -191,7 +193,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(smem_u32(&bars->tmem_full[a]), 1);
             mbar_init(smem_u32(&bars->tmem_empty[a]), 128u * (uint32_t)p.epi_groups);
         }
+        for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars->res_full[i]), 1);
         fence_barrier_init();
+        if (p.res_tma) prefetch_tmap(&map_res);
         if (!GATHER) prefetch_tmap(&map_a);
         prefetch_tmap(&map_bhi);
         if (p.three_x) prefetch_tmap(&map_blo);
@@ -232,7 +236,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t ss_base = epi_base + 32768u + (uint32_t)g * 4096u;
         const bool tracer = g == 0 && ew == 0 && lane == 0;
         const int chunk = lane & 7, rsub = lane >> 3;
-        uint32_t acc_it = 0, stg_it = 0;
+        uint32_t acc_it = 0, stg_it = 0, res_it = 0;
+        const uint32_t res_bar = smem_u32(&bars->res_full[g * 4 + ew]);
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++acc_it) {
             const int ks = t % p.k_splits, tt = t / p.k_splits;
             const int mp = tt / p.n_tiles, nt = tt - mp * p.n_tiles;
@@ -269,6 +274,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const bool tr = p.trace && t == cluster_id && c0 == 32 && tracer;
                 long long c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_4 = 0;
                 if (tr) c_0 = clock64();
+                if (p.res_tma && lane == 0) {
+                    // residual layers: the [32 rows x 32 columns] residual chunk travels by TMA into this chunk's staging buffer
+                    // while the accumulator is read and activated; the buffer's previous TMA store must have read it first
+                    if (ng == 1) tma_store_wait_read1();
+                    else tma_store_wait_read0();
+                    if (tile_ok) {
+                        mbar_arrive_expect_tx(res_bar, 4096u);
+                        tma_load_2d(stg, &map_res, res_bar, n0, m_base);   // rows >= M / columns >= N arrive as zeros
+                    }
+                }
                 tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
                 if (ncols == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
                 else {
@@ -302,8 +317,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
 #undef K2Y_EPI_LOOP
                     if (tr) c_2 = clock64();
-                    // the staging buffer used two chunks ago must have been read by its TMA store
-                    if (lane == 0) {
+                    if (p.res_tma) {
+                        if (tile_ok) {
+                            mbar_wait(res_bar, res_it & 1u);
+                            ++res_it;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {   // this lane's row of the residual chunk, same swizzle as the store below
+                                const float4 rr = ld_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4));
+                                r[j * 4] = __float_as_uint(__uint_as_float(r[j * 4]) + rr.x);
+                                r[j * 4 + 1] = __float_as_uint(__uint_as_float(r[j * 4 + 1]) + rr.y);
+                                r[j * 4 + 2] = __float_as_uint(__uint_as_float(r[j * 4 + 2]) + rr.z);
+                                r[j * 4 + 3] = __float_as_uint(__uint_as_float(r[j * 4 + 3]) + rr.w);
+                            }
+                        }
+                    } else if (lane == 0) {
+                        // the staging buffer used two chunks ago must have been read by its TMA store
                         if (ng == 1) tma_store_wait_read1();
                         else tma_store_wait_read0();
                     }
@@ -571,9 +599,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int iy = iy0 + ky, ix = ix0 + kx;
                     const bool ok = b >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
                     unsigned long long pr = 0ull;  // 0 = zero-fill (padding / rows beyond M)
-                    unsigned long long pr2 = 0ull; // half_taps: the second tap of the k-block (channels 16..31 of the block)
+                    unsigned long long pr2 = 0ull; // half_taps: the second tap of the k-block (upper half of its channels)
                     if (p.half_taps) {
-                        // k-block kb = taps 2 kb and 2 kb + 1, 16 channels (64 bytes) each; tap kh*kw (K padding) stays zero
+                        // k-block kb = taps 2 kb and 2 kb + 1, C0 channels each; tap kh*kw (K padding) stays zero
                         const int t0 = 2 * kb;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -603,13 +631,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (p.a_boxes == 2) {
                         const int cjj = lane & 15;
                         const uint32_t dcol = (uint32_t)(cjj >> 3) * A_TILE_BYTES;
+                        if (p.half_taps) {   // sub-tile 0 = first tap's 32 channels, sub-tile 1 = second tap's
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int lr = 2 * i + (lane >> 4);
-                            const unsigned long long q = __shfl_sync(0xffffffffu, pr, lr);
-                            const int row = wrow0 + lr;
-                            cp_async_16(stg_a + dcol + (uint32_t)row * 128u + (uint32_t)(((cjj & 7) ^ (row & 7)) << 4),
-                                        q ? (const void *)(q + (unsigned long long)cjj * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                            for (int i = 0; i < 16; ++i) {
+                                const int lr = 2 * i + (lane >> 4);
+                                const unsigned long long q0 = __shfl_sync(0xffffffffu, pr, lr);
+                                const unsigned long long q1 = __shfl_sync(0xffffffffu, pr2, lr);
+                                const unsigned long long q = (cjj & 8) ? q1 : q0;
+                                const int row = wrow0 + lr;
+                                cp_async_16(stg_a + dcol + (uint32_t)row * 128u + (uint32_t)(((cjj & 7) ^ (row & 7)) << 4),
+                                            q ? (const void *)(q + (unsigned long long)(cjj & 7) * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int lr = 2 * i + (lane >> 4);
+                                const unsigned long long q = __shfl_sync(0xffffffffu, pr, lr);
+                                const int row = wrow0 + lr;
+                                cp_async_16(stg_a + dcol + (uint32_t)row * 128u + (uint32_t)(((cjj & 7) ^ (row & 7)) << 4),
+                                            q ? (const void *)(q + (unsigned long long)cjj * 16ull) : (const void *)p.src0, q ? 16u : 0u);
+                            }
                         }
                     } else {
                         const int cjj = lane & 7;
@@ -1030,9 +1071,11 @@ void tc_free(TcWeights &w) {
 
 // bf16x3 needs whole 64-channel k-blocks per tap in the gather path; layers that do not fit run as 3xTF32
 static bool is_plain_1x1(const ConvArgs &a);
-// 3x3 (or any kh x kw > 1) conv over ONE plain 16-channel source: k-blocks of 32 = two taps of 16 channels
-static bool is_half_taps(const ConvArgs &a) {
-    return !is_plain_1x1(a) && a.C0 == 16 && a.C1 == 0 && a.src1 == nullptr && !a.up0;
+// Gather convs over ONE plain source whose channel count is HALF a k-block: the k-block then holds two consecutive taps —
+// 16 channels with the 32-wide tf32 k-blocks (tiny_yolo's 16->32 conv), 32 channels with the 64-wide bf16 k-blocks (the
+// 32-channel 3x3 convs of Darknet-53 and tiny_yolo), where each tap fills exactly one 16 KB sub-tile of the stage.
+static bool is_half_taps(const ConvArgs &a, int channels) {
+    return !is_plain_1x1(a) && a.C0 == channels && a.C1 == 0 && a.src1 == nullptr && !a.up0;
 }
 static int effective_mode(const ConvArgs &a, int math_mode) {
     if (math_mode != K2Y_MATH_TC_BF16X3) return math_mode;
@@ -1040,7 +1083,8 @@ static int effective_mode(const ConvArgs &a, int math_mode) {
     // (conv_pw_1 of yolo_mobilev1-0.75: 56 us as 3xTF32, 64 us as bf16x3); same error class
     if (is_plain_1x1(a)) return (a.C0 + a.C1 <= 32) ? K2Y_MATH_TC_3XTF32 : math_mode;
     const int Cin = a.C0 + a.C1;
-    return ((Cin % 64) == 0 && (a.C0 % 64) == 0) ? math_mode : K2Y_MATH_TC_3XTF32;
+    if ((Cin % 64) == 0 && (a.C0 % 64) == 0) return math_mode;
+    return is_half_taps(a, 32) ? math_mode : K2Y_MATH_TC_3XTF32;
 }
 
 static bool is_plain_1x1(const ConvArgs &a) {
@@ -1055,7 +1099,7 @@ bool tc_supported(const ConvArgs &a, const TcWeights &w) {
     if ((Cin % BK) == 0 && (a.C0 % BK) == 0)
         return (((uintptr_t)a.src0) & 15) == 0 && (a.src1 == nullptr || (((uintptr_t)a.src1) & 15) == 0);
     // ... or two 64-byte runs of two consecutive taps (Cin == 16, one plain source; runs as 3xTF32: effective_mode)
-    return is_half_taps(a) && (((uintptr_t)a.src0) & 15) == 0;
+    return is_half_taps(a, 16) && (((uintptr_t)a.src0) & 15) == 0;
 }
 
 // Depthwise 3x3 (+BN+act) followed by a plain 1x1 conv whose K fits one k-block: the depthwise result is produced straight
@@ -1124,7 +1168,7 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
     p.bf16 = (math_mode == K2Y_MATH_TC_BF16X3) ? 1 : 0;
     p.three_x = (math_mode == K2Y_MATH_TC_TF32) ? 0 : 1;
     p.a_boxes = p.bf16 ? 2 : 1;
-    p.half_taps = (!dw && is_half_taps(a)) ? 1 : 0;   // (never bf16: effective_mode sends Cin % 64 != 0 to 3xTF32)
+    p.half_taps = (!dw && is_half_taps(a, p.bf16 ? 32 : 16)) ? 1 : 0;
     p.nkb = p.bf16 ? w.Kpad64 / 64 : w.Kpad / BK;
     p.cluster = pick_cluster(p.M, p.nkb);
     pick_tile(p.M, a.N, p.nkb, p.three_x != 0, p.bf16 != 0, !is_plain_1x1(a) || dw, p.cluster, a.tc_scratch ? a.tc_scratch_bytes : 0,
@@ -1147,10 +1191,14 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
 
     const bool gather = !is_plain_1x1(a) || dw != nullptr;
     p.epi_groups = (!gather && p.BN > 32 && !getenv("K2Y_TC_ONE_EPI")) ? 2 : 1;
-    CUtensorMap map_a, map_bhi, map_blo, map_out;
+    CUtensorMap map_a, map_bhi, map_blo, map_out, map_res;
     memset(&map_a, 0, sizeof(map_a));
     memset(&map_out, 0, sizeof(map_out));
-    p.tma_store = ((a.N & 3) == 0 && a.residual == nullptr && (((uintptr_t)a.dst) & 15) == 0) ? 1 : 0;
+    memset(&map_res, 0, sizeof(map_res));
+    // TMA-store epilogue: 16-byte rows, and 32-column boxes that never reach into a neighbouring n-tile
+    p.tma_store = ((a.N & 3) == 0 && (((uintptr_t)a.dst) & 15) == 0 && (a.residual == nullptr || (((uintptr_t)a.residual) & 15) == 0) &&
+                   (p.n_tiles == 1 || (p.BN & 31) == 0)) ? 1 : 0;
+    p.res_tma = 0;
     if (getenv("K2Y_TC_NO_TMA_STORE") && p.k_splits == 1) p.tma_store = 0;
     const size_t mpad = (size_t)p.m_tiles * BM;
     float *scratch = a.tc_scratch;
@@ -1173,8 +1221,12 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         p.act_slope = 1.f;
         p.act_clamp = __int_as_float_host(0x7f800000);
         if (!make_map_2d(&map_out, scratch, (uint64_t)p.k_splits * mpad, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
-    } else if (p.tma_store && !make_map_2d(&map_out, a.dst, (uint64_t)p.M, (uint64_t)a.N, 32)) {
-        return cudaErrorInvalidValue;
+    } else if (p.tma_store) {
+        if (!make_map_2d(&map_out, a.dst, (uint64_t)p.M, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
+        if (a.residual) {
+            if (!make_map_2d(&map_res, a.residual, (uint64_t)p.M, (uint64_t)a.N, 32)) return cudaErrorInvalidValue;
+            p.res_tma = 1;
+        }
     }
     if (!gather && !make_map_2d(&map_a, a.src0, (uint64_t)p.M, (uint64_t)(a.C0 + a.C1), BM)) return cudaErrorInvalidValue;
     if (p.bf16) {
@@ -1215,9 +1267,9 @@ cudaError_t launch_conv_tc(const ConvArgs &a, const TcWeights &w, int math_mode,
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = (pdl_enabled() && !d_trace) ? 2 : 1;
-        cudaError_t le = dw       ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_bhi, map_blo, map_out, p)
-                         : gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_bhi, map_blo, map_out, p)
-                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, map_a, map_bhi, map_blo, map_out, p);
+        cudaError_t le = dw       ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_bhi, map_blo, map_out, map_res, p)
+                         : gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_bhi, map_blo, map_out, map_res, p)
+                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, map_a, map_bhi, map_blo, map_out, map_res, p);
         if (le != cudaSuccess) return le;
     }
     if (d_trace) {
@@ -1297,7 +1349,7 @@ extern "C" int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *b
     if (mode == K2Y_MATH_TC_BF16X3) {  // effective_mode(): same rules, expressed on (K, ksize)
         const int cin = gather ? K / 9 : K;
         if (!gather) mode = cin <= 32 ? K2Y_MATH_TC_3XTF32 : mode;
-        else if ((cin % 64) != 0) mode = K2Y_MATH_TC_3XTF32;
+        else if ((cin % 64) != 0 && cin != 32) mode = K2Y_MATH_TC_3XTF32;   // 32 channels: two taps per bf16 k-block
     }
     const bool bf = mode == K2Y_MATH_TC_BF16X3, three_x = mode != K2Y_MATH_TC_TF32;
     const int nkb = bf ? (K + 63) / 64 : (K + BK - 1) / BK;

@@ -79,6 +79,8 @@ SHAPES = [
     (1, 13, 13, 1024, 0, 0, 256, 1, 1, 0, 1, False),   # tiny_yolo 1x1 1024->256
     (2, 26, 30, 16, 0, 0, 32, 3, 1, 0, 1, False),      # tiny_yolo 3x3 16->32: two 16-channel taps per k-block, K = 144 padded to 160
     (1, 17, 19, 16, 0, 0, 48, 3, 2, 2, 1, False),      # same gather form, stride 2 with pad((1,0),(1,0)), odd extents
+    (2, 19, 21, 32, 0, 0, 64, 3, 1, 0, 1, True),       # darknet 3x3 32->64 resblock: two 32-channel taps per bf16 k-block, K = 288 -> 320
+    (1, 24, 20, 32, 0, 0, 64, 3, 2, 2, 1, False),      # darknet 3x3 32->64 stride 2
 ]
 
 

@@ -52,7 +52,8 @@ def test_planner_invariants(mode):
         elif ks == 1:
             assert p["math"] == (MATH_TC_3XTF32 if K <= 32 else MATH_TC_BF16X3)
         else:
-            assert p["math"] == (MATH_TC_BF16X3 if (K // 9) % 64 == 0 else MATH_TC_3XTF32)
+            # 3x3: whole 64-channel k-blocks per tap, or 32 channels (two taps per k-block); anything else runs as 3xTF32
+            assert p["math"] == (MATH_TC_BF16X3 if ((K // 9) % 64 == 0 or K // 9 == 32) else MATH_TC_3XTF32)
 
 
 def test_planner_rejects_bad_arguments():
