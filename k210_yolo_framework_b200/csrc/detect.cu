@@ -608,8 +608,8 @@ struct __align__(16) ChunkShared {
     float4 snbox[CHUNK_MAX];              // ... (min,max)-normalised
     float sarea[CHUNK_MAX];
     unsigned rows[CHUNK_MAX];             // warp 8+c's half of the rows of chunk c
-    float4 kbox[CHUNK_MAXK + 4];          // survivors so far, normalised (+4: the test loop reads in groups of four)
-    float karea[CHUNK_MAXK + 4];
+    float4 kbox[CHUNK_MAXK];              // survivors so far, normalised
+    float karea[CHUNK_MAXK];
     int cnt[CHUNK_MAX / 32];              // survivors after chunk c
 };
 constexpr size_t CHUNK_SMEM = (CHUNK_MAX + 4) * sizeof(unsigned long long) + sizeof(ChunkShared);   // arrival keys (padded to x4), tables
@@ -774,12 +774,15 @@ __device__ __forceinline__ void nms_chunked(const KerasParams &p, int n, const u
         named_sync(2 + (c & 1), nthr);
         const int total = cs.cnt[c];
         if (!removed) {
-            // against the survivors of chunk c, four independent straight-line tests at a time (entries past `total` are ignored)
+            // against the survivors of chunk c, four independent straight-line tests at a time; past the end the last survivor is
+            // tested again (never an entry >= total: the next chunk's warp may be writing those already)
             for (int k = base; k < total; k += 4) {
                 bool hit = false;
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    hit |= iou_norm_gt_sl(cs.kbox[k + u], cs.karea[k + u], nb, ar, p.iou) && (k + u < total);
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = min(k + u, total - 1);
+                    hit |= iou_norm_gt_sl(cs.kbox[kk], cs.karea[kk], nb, ar, p.iou);
+                }
                 if (hit) {
                     removed = true;
                     break;
