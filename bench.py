@@ -268,7 +268,8 @@ def run_ours(args, cfg):
     # `lanes` batches in flight, each on its own engine + streams (consecutive batches are independent: the early layers of one
     # run beside the small-grid late layers of the other); `pipe` = lane 0, used for every single-batch measurement below
     lp = LanedPipeline(args.lanes, cfg["model"], cfg["in_hw"], wl.anchors(cfg), cfg["classes"], cfg["alpha"], B, wl.OBJ_THRESH,
-                       wl.IOU_THRESH, wl.MAX_PER_CLASS, device=local, world=world, rank=rank)
+                       wl.IOU_THRESH, wl.MAX_PER_CLASS, device=local, world=world, rank=rank, sm_limit=args.lane_sms,
+                       max_queued=args.max_queued)
     pipe = lp.lanes[0]
     lp.set_weights(wl.bench_weights(cfg, pipe.engine.expected_variables()))
     lp.set_math(math_modes[args.math])
@@ -339,9 +340,13 @@ def run_ours(args, cfg):
     if rank == 0:
         sampler.start()
         time.sleep(0.5)
-    for i in range(args.warmup):
+    # W warm-up steps through the very path that is timed (lane streams, decode streams, collectives), after a settling run of the
+    # same kind: with more than one rank the first few dozen steps after start-up run slower (observed on 2 GPUs: a 30-step
+    # window right after 5 warm-up steps measured 0.54 ms per step, the windows after it 0.42-0.45 ms)
+    for i in range(40 + args.warmup):
         lp.bind_input(xs[i % n_in])
         lp.step_device()
+    lp.wait_all()
     dev_ms = timed_steps(args.steps)
 
     # ---- end to end: pinned host input -> H2D -> step -> D2H records ----------------------------
@@ -402,6 +407,10 @@ def run_ours(args, cfg):
     if args.math != "tc_3xtf32":
         lp.set_math(math_modes["tc_3xtf32"])
         capture_all()
+        for i in range(20):                 # settle on the timed path, as above
+            lp.bind_input(xs[i % n_in])
+            lp.step_device()
+        lp.wait_all()
         m_steps = min(args.steps, 20)
         m_ms = timed_steps(m_steps)
         matched = {"math": "tc_3xtf32", "steps": m_steps, "ms": m_ms}
@@ -513,7 +522,7 @@ def run_ours(args, cfg):
             "arm": {"math": args.math,
                     "parallelism": f"image-shard x{world}" + (", one ncclAllGather per step on a side stream" if world > 1 else ""),
                     "l2": f"{n_in} distinct device-resident input batches in rotation ({n_in * in_bytes >> 20} MiB > 126 MiB L2), no flush inside the window",
-                    "lanes": args.lanes, "lane_sm_budget": lane_sm_limit or "whole device",
+                    "lanes": args.lanes, "lane_sm_budget": lane_sm_limit or "whole device", "max_queued_batches": lp.max_queued,
                     "streams": f"{args.lanes} batches in flight, one lane (engine + arena + streams) each, fed round-robin: a lane runs "
                                "its network graph on its compute stream and decode + NMS on a second stream (two head-buffer sets); "
                                "every lane's last decode is inside the timed window",
@@ -560,6 +569,8 @@ def main():
     ap.add_argument("--math", choices=["fp32_simt", "tc_3xtf32", "tc_tf32", "tc_bf16x3"], default=os.environ.get("K2Y_BENCH_MATH", "tc_bf16x3"))
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("K2Y_BENCH_LANES", "2")),
                     help="batches in flight on one GPU (each lane = engine + activation arena + streams); 1 = strictly one batch at a time")
+    ap.add_argument("--lane-sms", type=int, default=None, help="SM budget of each lane's tensor-core kernels (default: SMs / lanes; 0 = whole device)")
+    ap.add_argument("--max-queued", type=int, default=None, help="device-resident loop: batches the host may run ahead of the GPU (default 2 per lane)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs (profiling runs)")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run exactly one step between cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -180,7 +180,7 @@ class LanedPipeline:
     ``bind_input(x)`` / ``step_device()`` / ``wait_all()`` for device-resident inputs, ``submit`` / ``collect`` for pinned
     host batches (tickets carry the lane)."""
 
-    def __init__(self, lanes: int, *args, sm_split: bool = True, **kw):
+    def __init__(self, lanes: int, *args, sm_split: bool = True, sm_limit: Optional[int] = None, max_queued: Optional[int] = None, **kw):
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
         first = DetectionPipeline(*args, **kw)
@@ -192,11 +192,22 @@ class LanedPipeline:
         self._next = 0          # next lane for step_device
         self._next_host = 0     # next lane for submit
         self._ran = [False] * lanes
+        # host-side flow control of step_device: at most `max_queued` batches issued and not yet through their network — a bounded
+        # queue, as a server has.  Default 2 per lane (= the gather / head-set slots of a lane, and what submit/collect allows):
+        # the GPU always has a full step queued behind the running one, and the host never runs further ahead.  Deeper queues
+        # measured WORSE with more than one rank (8 or unbounded: 119 k images/s on 2 GPUs, 4: 152 k — profiles/r02_lanes.md).
+        self.max_queued = max(lanes, int(max_queued)) if max_queued is not None else 2 * lanes
+        self._flow_events = [torch.cuda.Event() for _ in range(self.max_queued)]
+        self._flow_pending = 0
+        self._issued = 0
         # each lane plans its persistent tensor-core kernels for 1/lanes of the SMs: two lanes' one-CTA-per-SM grids then run
         # side by side (measured on cfg 2, two lanes: 69.3 k -> 77 k images/s; see profiles/r02_lanes.md)
         self.sm_limit = 0
-        if sm_split and lanes > 1:
+        if sm_limit is not None:
+            self.sm_limit = int(sm_limit)
+        elif sm_split and lanes > 1:
             self.sm_limit = torch.cuda.get_device_properties(dev).multi_processor_count // lanes
+        if self.sm_limit:
             for ln in self.lanes:
                 ln.engine.set_sm_limit(self.sm_limit)
 
@@ -225,8 +236,13 @@ class LanedPipeline:
         self._fork.record(cur)
         st = self._streams[k]
         st.wait_event(self._fork)
+        slot = self._issued % self.max_queued
+        if self._issued >= self.max_queued:
+            self._flow_events[slot].synchronize()     # the batch issued max_queued steps ago has left its network
         with torch.cuda.stream(st):
             views = self.lanes[k].step_device(n, pipelined=True)
+            self._flow_events[slot].record(st)
+        self._issued += 1
         self._ran[k] = True
         return views
 
