@@ -208,6 +208,9 @@ int k2y_region_run(const k2y_region_cfg *cfg, const float *in_dev, int batch, fl
  * and the arithmetic mode the layer really runs in. */
 int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *bn, int *k_splits, int *stages, int *cluster,
                 int *effective_math);
+/* The same under an SM budget (k2y_net_set_sm_limit; 0 = whole device); also reports the persistent grid size (CTAs). */
+int k2y_tc_plan_budget(int M, int N, int K, int ksize, int math_mode, int sm_limit, int *bn, int *k_splits, int *stages,
+                       int *cluster, int *effective_math, int *grid);
 
 /* ------------------------------------------------------------------------------------------
  * Operator-level pieces of the reference's decode loop, for callers that keep keras_inference.py:94-135 and swap one

@@ -96,6 +96,7 @@ _SIGNATURES = {
     "k2y_region_run": (c_int, [POINTER(RegionCfg), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
     "k2y_tc_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "k2y_tc_plan_budget": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "k2y_xywh_to_all": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, POINTER(c_float), c_void_p, c_void_p, c_void_p]),
     "k2y_correct_box": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
     "k2y_nms_workspace_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),

@@ -1336,11 +1336,21 @@ size_t tc_scratch_bound(const ConvArgs &a, const TcWeights &w) {
 
 // Host-only view of the tile planner (no GPU needed: without a device it assumes a B200 — 148 SMs, 227 KB of shared
 // memory): which tile width, split-K factor, pipeline depth and CTA-pair mode a dense conv of this GEMM shape gets.
+extern "C" int k2y_tc_plan_budget(int M, int N, int K, int ksize, int math_mode, int sm_limit, int *bn, int *k_splits, int *stages,
+                                  int *cluster, int *effective_math, int *grid);
+
 extern "C" int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *bn, int *k_splits, int *stages, int *cluster,
                            int *effective_math) {
+    int grid = 0;
+    return k2y_tc_plan_budget(M, N, K, ksize, math_mode, 0, bn, k_splits, stages, cluster, effective_math, &grid);
+}
+
+// The same view under an SM budget (k2y_net_set_sm_limit): also reports the persistent grid size.
+extern "C" int k2y_tc_plan_budget(int M, int N, int K, int ksize, int math_mode, int sm_limit, int *bn, int *k_splits, int *stages,
+                                  int *cluster, int *effective_math, int *grid) {
     using namespace k2y;
     if (M <= 0 || N <= 0 || K <= 0 || (ksize != 1 && ksize != 3) || !bn || !k_splits || !stages || !cluster || !effective_math ||
-        (math_mode != K2Y_MATH_TC_3XTF32 && math_mode != K2Y_MATH_TC_TF32 && math_mode != K2Y_MATH_TC_BF16X3)) {
+        (math_mode != K2Y_MATH_TC_3XTF32 && math_mode != K2Y_MATH_TC_TF32 && math_mode != K2Y_MATH_TC_BF16X3) || sm_limit < 0 || !grid) {
         set_error("k2y_tc_plan: bad arguments");
         return K2Y_ERR_INVALID;
     }
@@ -1354,7 +1364,8 @@ extern "C" int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *b
     const bool bf = mode == K2Y_MATH_TC_BF16X3, three_x = mode != K2Y_MATH_TC_TF32;
     const int nkb = bf ? (K + 63) / 64 : (K + BK - 1) / BK;
     *cluster = pick_cluster(M, nkb);
-    pick_tile(M, N, nkb, three_x, bf, gather, *cluster, 0, budget_sms(0), bn, k_splits);
+    const int sms = budget_sms(sm_limit);
+    pick_tile(M, N, nkb, three_x, bf, gather, *cluster, 0, sms, bn, k_splits);
     const size_t stage_bytes = (size_t)A_TILE_BYTES * (bf ? 2 : 1) + (size_t)(*bn) * 128 * (three_x ? 2 : 1);
     int st = (int)(((g_max_smem ? g_max_smem : 232448) - FIXED_SMEM) / stage_bytes);
     if (st > MAX_STAGES) st = MAX_STAGES;
@@ -1363,6 +1374,11 @@ extern "C" int k2y_tc_plan(int M, int N, int K, int ksize, int math_mode, int *b
     const int kb_per_split = (nkb + *k_splits - 1) / *k_splits;
     *k_splits = (nkb + kb_per_split - 1) / kb_per_split;
     *effective_math = mode;
+    {
+        const int n16 = (N + 15) / 16 * 16, n_tiles = (n16 + *bn - 1) / *bn, m_tiles = (M + BM - 1) / BM;
+        const int items = ((m_tiles + *cluster - 1) / *cluster) * n_tiles * *k_splits, max_clusters = sms / *cluster;
+        *grid = (items < max_clusters ? items : max_clusters) * *cluster;
+    }
     return K2Y_OK;
 }
 

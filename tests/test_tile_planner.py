@@ -63,3 +63,42 @@ def test_planner_rejects_bad_arguments():
         plan(128, 48, 24, 2)
     with pytest.raises(K2YError):
         plan(128, 48, 24, 1, mode=0)    # the fp32 CUDA-core mode has no tiles to plan
+
+
+def plan_budget(M, N, K, ksize, sm_limit, mode=MATH_TC_BF16X3):
+    v = [ctypes.c_int() for _ in range(6)]
+    check(lib.k2y_tc_plan_budget(M, N, K, ksize, mode, sm_limit, *[ctypes.byref(x) for x in v]))
+    return dict(zip(("bn", "splits", "stages", "cluster", "math", "grid"), (x.value for x in v)))
+
+
+# every tensor-core GEMM of cfg 2 (yolo_mobilev1-0.75 at batch 32): (M, N, K, ksize)
+CFG2_GEMMS = [(286720, 96, 48, 1), (143360, 96, 48, 1), (143360, 96, 96, 1), (35840, 192, 96, 1), (35840, 192, 192, 1), (8960, 384, 192, 1),
+              (8960, 384, 384, 1), (2240, 768, 384, 1), (2240, 768, 768, 1), (2240, 192, 6912, 3), (2240, 75, 192, 1), (2240, 128, 768, 1),
+              (8960, 128, 4608, 3), (8960, 75, 128, 1)]
+
+
+@pytest.mark.parametrize("sm_limit", [0, 74, 72, 48, 9])
+def test_planner_under_sm_budget(sm_limit):
+    """k2y_net_set_sm_limit: the persistent grid never exceeds the budget (rounded down to even, at least 8), and every layer of
+    the headline network still gets a tile that fits shared memory and tensor memory."""
+    budget = 148 if sm_limit in (0,) or sm_limit >= 148 else max(8, sm_limit) & ~1
+    for M, N, K, ks in CFG2_GEMMS:
+        p = plan_budget(M, N, K, ks, sm_limit)
+        assert 1 <= p["grid"] <= budget and p["grid"] % p["cluster"] == 0
+        assert 2 <= p["stages"] <= 8 and 16 <= p["bn"] <= 256
+        three_x = p["math"] != MATH_TC_TF32
+        if three_x:
+            assert 2 * p["bn"] + 64 * p["stages"] <= 512
+        a_bytes = 32768 if p["math"] == MATH_TC_BF16X3 else 16384
+        assert p["stages"] * (a_bytes + p["bn"] * 128 * (2 if three_x else 1)) + 43400 <= 232448
+        if sm_limit == 0:
+            q = plan(M, N, K, ks)
+            assert {k: p[k] for k in q} == q        # budget 0 = the plain planner
+
+
+def test_budget_uses_its_whole_share_on_the_small_grid_layers():
+    # conv_pw_7..11 (70 m-tiles x n-tiles): on the whole device one CTA per SM, on a 74-SM share 74 CTAs with more tiles each
+    assert plan_budget(8960, 384, 384, 1, 0)["grid"] > 100
+    assert plan_budget(8960, 384, 384, 1, 74)["grid"] == 74
+    with pytest.raises(K2YError):
+        plan_budget(8960, 384, 384, 1, -1)
